@@ -1,0 +1,249 @@
+/*
+ * sgtd_b200.h -- C ABI of libsgtd_b200.so: the B200 (sm_100a) implementation
+ * of SGTD's one-shot global-localization hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one piece of the
+ * reference's descriptor-manager surface (paths relative to
+ * /root/reference/src/sgtd, "R/"):
+ *
+ *   sgtd_config / sgtd_config_default / sgtd_config_from_yaml
+ *        <- ConfigSetting + read_parameters      R/include/desc/STDesc.h:38-72
+ *                                                R/src/STDesc.cpp:18-70
+ *                                                R/config/SG_localization.yaml:59-88
+ *   sgtd_create / sgtd_destroy
+ *        <- STDescManager::STDescManager(cfg)    R/include/desc/STDesc.h:362-367
+ *   sgtd_build_descriptors
+ *        <- STDescManager::BuildSingleScanSTD    R/src/STDesc.cpp:174-315
+ *   sgtd_add_descriptors (+ lazy sgtd_finalize_db)
+ *        <- STDescManager::AddSTDescs            R/src/STDesc.cpp:149-172
+ *   sgtd_search
+ *        <- STDescManager::SearchLoop            R/src/STDesc.cpp:84-147
+ *           = candidate_selector (:318-460) + candidate_verify (:462-547)
+ *             + triangle_solver (:549-571)
+ *   sgtd_extract_instances
+ *        <- gen_labels + gen_graphs              R/src/get_json.cpp:41-343
+ *           clusterManager::segmentPointCloud    R/include/cluster_manager.hpp:139-421
+ *   sgtd_shard_init
+ *        <- (no reference equivalent; keyframe-range sharding of data_base_)
+ *
+ * Conventions: plain pointers and sizes, no exceptions, no STL, no torch types.
+ * Every function returns an sgtd_status (0 = OK) unless noted.  Input pointers
+ * may be host or device memory (detected with cudaPointerGetAttributes); they
+ * are consumed before the call returns.  There is NO CPU fallback: if no CUDA
+ * device is usable sgtd_create fails with SGTD_E_CUDA.
+ */
+#ifndef SGTD_B200_H
+#define SGTD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGTD_ABI_VERSION 1
+
+typedef enum sgtd_status {
+  SGTD_OK = 0,
+  SGTD_E_INVALID = 1,       /* bad argument                                   */
+  SGTD_E_TOO_FEW_NODES = 2, /* a scan has fewer nodes than descriptor_near_num
+                               (the reference reads stale indices here)       */
+  SGTD_E_CAPACITY = 3,      /* a caller-provided buffer is too small          */
+  SGTD_E_CUDA = 4,          /* CUDA runtime error, see sgtd_last_error        */
+  SGTD_E_NCCL = 5,
+  SGTD_E_EMPTY = 6,         /* "No STDescs!" (R/src/STDesc.cpp:89-93)         */
+  SGTD_E_IO = 7
+} sgtd_status;
+
+/* Field-for-field mirror of ConfigSetting (R/include/desc/STDesc.h:38-72).
+ * Only the fields marked (live) are read by the path. */
+typedef struct sgtd_config {
+  int32_t stop_skip_enable;
+  double ds_size;
+  int32_t maximum_corner_num;
+  double plane_merge_normal_thre;
+  double plane_merge_dis_thre;
+  double plane_detection_thre;
+  double voxel_size;
+  int32_t voxel_init_num;
+  double proj_image_resolution;
+  double proj_dis_min;
+  double proj_dis_max;
+  double corner_thre;
+  int32_t descriptor_near_num;     /* (live) 10   */
+  double descriptor_min_len;       /* (live) 0.5  */
+  double descriptor_max_len;       /* (live) 50   */
+  double non_max_suppression_radius;
+  double std_side_resolution;      /* (live) 1    */
+  int32_t skip_near_num;
+  int32_t candidate_num;           /* (live) 50   */
+  int32_t sub_frame_num;
+  double rough_dis_threshold;      /* (live) 0.03 */
+  double vertex_diff_threshold;
+  double icp_threshold;            /* (live) 0.4  */
+  double normal_threshold;
+  double dis_threshold;
+} sgtd_config;
+
+/* One instance node == one pcl::PointXYZL of the node cloud that
+ * Graph2CloudL builds (R/include/utility.hpp:646-659). */
+typedef struct sgtd_node {
+  float x, y, z;
+  uint32_t label;
+} sgtd_node;
+
+/* Compact STDesc (R/include/desc/STDesc.h:75-97), 72 bytes, host exchange
+ * format.  center_ is (A+B+C)/3 and angle_/cov_mat_* are never read downstream,
+ * so they are not stored. */
+typedef struct sgtd_desc {
+  double side[3];  /* side_length_ (scale * sorted side lengths)           */
+  float vert[9];   /* vertex_A_, vertex_B_, vertex_C_ (exact float values) */
+  uint32_t frame;  /* frame_id_                                            */
+  uint8_t lab[3];  /* vertex_attached_                                     */
+  uint8_t pad;
+  uint16_t anchor; /* node_id = {anchor, m, n}                             */
+  uint8_t m, n;
+} sgtd_desc;
+
+/* One verified candidate == one LOOP_RESULT (R/include/desc/STDesc.h:99-104). */
+typedef struct sgtd_candidate {
+  int32_t frame;      /* match_id (global keyframe id)                       */
+  int32_t votes;      /* rough-match votes of that keyframe                  */
+  int32_t nmatch;     /* |match_list_| (== votes)                            */
+  int32_t score;      /* match_fitness: #inliers, or -1 if < 4 hypothesis votes */
+  int64_t match_off;  /* offset of this candidate's match list (this rank),
+                         -1 if another shard owns the keyframe               */
+  int32_t ninlier;
+  int32_t best_hyp;   /* winning hypothesis index, -1 if none                */
+  double R[9];        /* loop_transform.second, row-major                    */
+  double t[3];        /* loop_transform.first                                */
+  int64_t inlier_off; /* offset into the inlier index array                  */
+} sgtd_candidate;
+
+/* loop_result of SearchLoop for one query: (frame or -1, score). */
+typedef struct sgtd_loop_result {
+  int32_t frame;
+  int32_t ncand;
+  double score;
+} sgtd_loop_result;
+
+/* Work counters of the vote kernel (for the roofline's algorithmic bytes:
+ * bytes = 32*Q + 16*P + 28*E + 12*M). */
+typedef struct sgtd_vote_stats {
+  int64_t Q, P, Pfound, E, M;
+} sgtd_vote_stats;
+
+/* Per-stage device times of the last sgtd_search, milliseconds (CUDA events on
+ * the handle's stream). */
+typedef struct sgtd_timings {
+  float vote_ms, topk_ms, exchange_ms, collect_ms, verify_ms, total_ms;
+  int32_t vote_launches, total_launches;
+} sgtd_timings;
+
+typedef struct sgtd_handle sgtd_handle;
+typedef struct sgtd_desc_batch sgtd_desc_batch;     /* device-resident descriptors */
+typedef struct sgtd_search_result sgtd_search_result; /* device-resident results   */
+
+/* ---- version / config ---------------------------------------------------- */
+int sgtd_abi_version(void);
+const char *sgtd_status_string(int status);
+int sgtd_config_default(sgtd_config *cfg); /* values of SG_localization.yaml   */
+int sgtd_config_from_yaml(const char *path, sgtd_config *cfg); /* flat keys    */
+
+/* ---- lifetime ------------------------------------------------------------ */
+int sgtd_create(const sgtd_config *cfg, int device, sgtd_handle **out);
+int sgtd_destroy(sgtd_handle *h);
+const char *sgtd_last_error(const sgtd_handle *h);
+uint32_t sgtd_current_frame_id(const sgtd_handle *h); /* current_frame_id_     */
+int64_t sgtd_db_size(const sgtd_handle *h);           /* descriptors on this rank */
+void *sgtd_stream(const sgtd_handle *h);              /* cudaStream_t of the handle */
+int sgtd_synchronize(sgtd_handle *h);
+int64_t sgtd_kernel_launches(const sgtd_handle *h);   /* kernels launched so far */
+
+/* ---- stage 2: triangle descriptors --------------------------------------- */
+/* nodes of scan s are nodes[scan_offsets[s] .. scan_offsets[s+1]).  frame_ids
+ * may be NULL: every descriptor then carries current_frame_id_ (what
+ * BuildSingleScanSTD does).  The result stays on the device. */
+int sgtd_build_descriptors(sgtd_handle *h, const sgtd_node *nodes,
+                           const int64_t *scan_offsets, int32_t nscans,
+                           const uint32_t *frame_ids, sgtd_desc_batch **out);
+int sgtd_desc_batch_upload(sgtd_handle *h, const sgtd_desc *descs,
+                           const int64_t *scan_offsets, int32_t nscans,
+                           sgtd_desc_batch **out);
+int64_t sgtd_desc_batch_size(const sgtd_desc_batch *b);
+int32_t sgtd_desc_batch_scans(const sgtd_desc_batch *b);
+/* offsets: nscans+1 entries (host).  descs may be NULL to fetch offsets only. */
+int sgtd_desc_batch_download(sgtd_handle *h, const sgtd_desc_batch *b,
+                             sgtd_desc *descs, int64_t *offsets);
+int sgtd_desc_batch_free(sgtd_desc_batch *b);
+
+/* ---- stage 3: database ----------------------------------------------------- */
+/* Each scan of the batch becomes one keyframe: current_frame_id_ advances by
+ * nscans.  On a sharded handle only the keyframes this rank owns are stored;
+ * every rank must be given the same batches. */
+int sgtd_add_descriptors(sgtd_handle *h, const sgtd_desc_batch *b);
+int sgtd_reserve(sgtd_handle *h, int64_t n_desc, int64_t n_frames);
+int sgtd_finalize_db(sgtd_handle *h); /* sort + bucket table; implicit in search */
+/* 64-bit database key of one descriptor as sgtd_add_descriptors forms it. */
+uint64_t sgtd_db_key(const sgtd_config *cfg, const sgtd_desc *d);
+
+/* ---- stages 3+4: search ----------------------------------------------------- */
+/* One SearchLoop per scan of `queries`.  Query descriptors should carry
+ * frame == current_frame_id_ (the reference's convention). */
+int sgtd_search(sgtd_handle *h, const sgtd_desc_batch *queries,
+                sgtd_search_result **out);
+int32_t sgtd_result_queries(const sgtd_search_result *r);
+/* loops: nq entries; cands: nq * candidate_num entries (entry c of query q at
+ * q*candidate_num + c, valid for c < loops[q].ncand).  Either may be NULL. */
+int sgtd_result_download(sgtd_handle *h, const sgtd_search_result *r,
+                         sgtd_loop_result *loops, sgtd_candidate *cands);
+/* Match list of candidate c of query q (owned candidates only): query
+ * descriptor index within the query, probe ordinal 0..26, global DB descriptor
+ * index (keyframe-major insertion order).  cap = capacity in entries. */
+int sgtd_result_matches(sgtd_handle *h, const sgtd_search_result *r, int32_t q,
+                        int32_t c, int32_t *m_q, uint8_t *m_cell, uint32_t *m_g,
+                        int64_t cap);
+int sgtd_result_inliers(sgtd_handle *h, const sgtd_search_result *r, int32_t q,
+                        int32_t c, int32_t *inl, int64_t cap);
+/* votes of query q for keyframes [0, n_frames) of this rank's range. */
+int sgtd_result_votes(sgtd_handle *h, const sgtd_search_result *r, int32_t q,
+                      int32_t *votes, int64_t n_frames);
+int sgtd_result_stats(sgtd_handle *h, const sgtd_search_result *r,
+                      sgtd_vote_stats *stats, sgtd_timings *timings);
+int sgtd_result_free(sgtd_search_result *r);
+/* Fetch DB descriptors by global index (to build loop_std_pair). */
+int sgtd_db_fetch(sgtd_handle *h, const uint32_t *g, int64_t n, sgtd_desc *out);
+
+/* ---- host-side deterministic top-k merge (same code the GPU merge runs) ---- */
+/* lists: nlists arrays of k (votes, frame) pairs, votes==0 marks an empty
+ * slot.  Writes the k best by (votes desc, frame asc) to out_*. */
+int sgtd_merge_topk_host(const int32_t *votes, const int32_t *frames,
+                         int32_t nlists, int32_t k, int32_t *out_votes,
+                         int32_t *out_frames);
+
+/* ---- multi-GPU: keyframe-range shards -------------------------------------- */
+/* Rank r of nranks owns keyframes [r*frames_per_rank, (r+1)*frames_per_rank).
+ * nccl_unique_id: the 128-byte ncclUniqueId produced on rank 0 by
+ * sgtd_nccl_unique_id and distributed by the caller (any transport).
+ * nranks == 1 or nccl_unique_id == NULL: no communicator (single shard, or
+ * "virtual shards": nvshards handles in one process merged by the caller). */
+int sgtd_nccl_unique_id(void *id128);
+int sgtd_shard_init(sgtd_handle *h, int32_t rank, int32_t nranks,
+                    int64_t frames_per_rank, const void *nccl_unique_id);
+
+/* ---- stage 1: instance extraction ------------------------------------------ */
+/* points: n x float4 (x,y,z,intensity) as in a KITTI .bin; labels: n x uint32
+ * (lo16 semantic train id, hi16 instance id) as in a .label file.
+ * Outputs (host buffers, capacities in elements): point_instance[n] = instance
+ * id of each point or -1; nodes[cap_nodes] = graph nodes (label after node_map,
+ * centroid); *n_nodes, *n_instances.  */
+int sgtd_extract_instances(sgtd_handle *h, const float *points,
+                           const uint32_t *labels, int64_t n,
+                           int32_t *point_instance, sgtd_node *nodes,
+                           int32_t cap_nodes, int32_t *n_nodes,
+                           int32_t *n_instances);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGTD_B200_H */

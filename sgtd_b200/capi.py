@@ -1,0 +1,344 @@
+"""ctypes binding of include/sgtd_b200.h (libsgtd_b200.so).
+
+This is plumbing for tests and bench.py: every call goes through the C ABI a
+C++ host (the reference's ROS node) would bind.  There is no Python or CPU
+fallback: if the shared library is missing, import fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsgtd_b200.so")
+
+DESC_DTYPE = np.dtype(
+    [("side", "<f8", 3), ("vert", "<f4", 9), ("frame", "<u4"), ("lab", "u1", 3),
+     ("pad", "u1"), ("anchor", "<u2"), ("m", "u1"), ("n", "u1")], align=False)
+NODE_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("label", "<u4")])
+CAND_DTYPE = np.dtype(
+    [("frame", "<i4"), ("votes", "<i4"), ("nmatch", "<i4"), ("score", "<i4"),
+     ("match_off", "<i8"), ("ninlier", "<i4"), ("best_hyp", "<i4"),
+     ("R", "<f8", 9), ("t", "<f8", 3), ("inlier_off", "<i8")], align=False)
+LOOP_DTYPE = np.dtype([("frame", "<i4"), ("ncand", "<i4"), ("score", "<f8")])
+assert DESC_DTYPE.itemsize == 72 and NODE_DTYPE.itemsize == 16
+assert CAND_DTYPE.itemsize == 136 and LOOP_DTYPE.itemsize == 16
+
+OK, E_INVALID, E_TOO_FEW_NODES, E_CAPACITY, E_CUDA, E_NCCL, E_EMPTY, E_IO = range(8)
+
+
+class Config(C.Structure):
+    """Mirror of sgtd_config == ConfigSetting (R/include/desc/STDesc.h:38-72)."""
+    _fields_ = [
+        ("stop_skip_enable", C.c_int32), ("ds_size", C.c_double), ("maximum_corner_num", C.c_int32),
+        ("plane_merge_normal_thre", C.c_double), ("plane_merge_dis_thre", C.c_double),
+        ("plane_detection_thre", C.c_double), ("voxel_size", C.c_double), ("voxel_init_num", C.c_int32),
+        ("proj_image_resolution", C.c_double), ("proj_dis_min", C.c_double), ("proj_dis_max", C.c_double),
+        ("corner_thre", C.c_double), ("descriptor_near_num", C.c_int32), ("descriptor_min_len", C.c_double),
+        ("descriptor_max_len", C.c_double), ("non_max_suppression_radius", C.c_double),
+        ("std_side_resolution", C.c_double), ("skip_near_num", C.c_int32), ("candidate_num", C.c_int32),
+        ("sub_frame_num", C.c_int32), ("rough_dis_threshold", C.c_double), ("vertex_diff_threshold", C.c_double),
+        ("icp_threshold", C.c_double), ("normal_threshold", C.c_double), ("dis_threshold", C.c_double)]
+
+
+class VoteStats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("Q", "P", "Pfound", "E", "M")]
+
+
+class Timings(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("vote_ms", "topk_ms", "exchange_ms", "collect_ms", "verify_ms", "total_ms")] + \
+               [("vote_launches", C.c_int32), ("total_launches", C.c_int32)]
+
+
+# every symbol include/sgtd_b200.h declares: (restype, argtypes)
+_VP, _I32, _I64, _U32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+SYMBOLS = {
+    "sgtd_abi_version": (C.c_int, []),
+    "sgtd_status_string": (C.c_char_p, [C.c_int]),
+    "sgtd_config_default": (C.c_int, [C.POINTER(Config)]),
+    "sgtd_config_from_yaml": (C.c_int, [C.c_char_p, C.POINTER(Config)]),
+    "sgtd_create": (C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(_VP)]),
+    "sgtd_destroy": (C.c_int, [_VP]),
+    "sgtd_last_error": (C.c_char_p, [_VP]),
+    "sgtd_current_frame_id": (_U32, [_VP]),
+    "sgtd_db_size": (_I64, [_VP]),
+    "sgtd_stream": (_VP, [_VP]),
+    "sgtd_synchronize": (C.c_int, [_VP]),
+    "sgtd_kernel_launches": (_I64, [_VP]),
+    "sgtd_build_descriptors": (C.c_int, [_VP, _VP, _VP, _I32, _VP, C.POINTER(_VP)]),
+    "sgtd_desc_batch_upload": (C.c_int, [_VP, _VP, _VP, _I32, C.POINTER(_VP)]),
+    "sgtd_desc_batch_size": (_I64, [_VP]),
+    "sgtd_desc_batch_scans": (_I32, [_VP]),
+    "sgtd_desc_batch_download": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "sgtd_desc_batch_free": (C.c_int, [_VP]),
+    "sgtd_add_descriptors": (C.c_int, [_VP, _VP]),
+    "sgtd_reserve": (C.c_int, [_VP, _I64, _I64]),
+    "sgtd_finalize_db": (C.c_int, [_VP]),
+    "sgtd_db_key": (C.c_uint64, [C.POINTER(Config), _VP]),
+    "sgtd_search": (C.c_int, [_VP, _VP, C.POINTER(_VP)]),
+    "sgtd_result_queries": (_I32, [_VP]),
+    "sgtd_result_download": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "sgtd_result_matches": (C.c_int, [_VP, _VP, _I32, _I32, _VP, _VP, _VP, _I64]),
+    "sgtd_result_inliers": (C.c_int, [_VP, _VP, _I32, _I32, _VP, _I64]),
+    "sgtd_result_votes": (C.c_int, [_VP, _VP, _I32, _VP, _I64]),
+    "sgtd_result_stats": (C.c_int, [_VP, _VP, C.POINTER(VoteStats), C.POINTER(Timings)]),
+    "sgtd_result_free": (C.c_int, [_VP]),
+    "sgtd_db_fetch": (C.c_int, [_VP, _VP, _I64, _VP]),
+    "sgtd_merge_topk_host": (C.c_int, [_VP, _VP, _I32, _I32, _VP, _VP]),
+    "sgtd_nccl_unique_id": (C.c_int, [_VP]),
+    "sgtd_shard_init": (C.c_int, [_VP, _I32, _I32, _I64, _VP]),
+    "sgtd_extract_instances": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _VP, _I32, _VP, _VP]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libsgtd_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C sgtd_b200/csrc`.  sgtd_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the ABI symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class SgtdError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"[{status}] {msg}")
+        self.status = status
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))  # raw device pointer
+
+
+def default_config(**over):
+    c = Config()
+    lib().sgtd_config_default(C.byref(c))
+    for k, v in over.items():
+        setattr(c, k, v)
+    return c
+
+
+def config_from_yaml(path):
+    c = Config()
+    rc = lib().sgtd_config_from_yaml(path.encode(), C.byref(c))
+    if rc:
+        raise SgtdError(rc, f"cannot read {path}")
+    return c
+
+
+def merge_topk_host(votes, frames, k):
+    """votes/frames: int32 [nlists, k] -> (votes[k], frames[k])."""
+    votes = np.ascontiguousarray(votes, np.int32)
+    frames = np.ascontiguousarray(frames, np.int32)
+    nl = votes.size // k
+    ov = np.zeros(k, np.int32)
+    of = np.zeros(k, np.int32)
+    rc = lib().sgtd_merge_topk_host(_p(votes), _p(frames), nl, k, _p(ov), _p(of))
+    if rc:
+        raise SgtdError(rc, "sgtd_merge_topk_host")
+    return ov, of
+
+
+def db_key(desc, cfg=None):
+    cfg = cfg or default_config()
+    d = np.ascontiguousarray(desc, DESC_DTYPE).reshape(1)
+    return int(lib().sgtd_db_key(C.byref(cfg), _p(d)))
+
+
+class DescBatch:
+    def __init__(self, mgr, ptr):
+        self.mgr, self.ptr = mgr, ptr
+
+    def __len__(self):
+        return int(lib().sgtd_desc_batch_size(self.ptr))
+
+    @property
+    def nscans(self):
+        return int(lib().sgtd_desc_batch_scans(self.ptr))
+
+    def download(self, want_descs=True):
+        n, ns = len(self), self.nscans
+        off = np.zeros(ns + 1, np.int64)
+        descs = np.zeros(n, DESC_DTYPE) if want_descs else None
+        self.mgr._chk(lib().sgtd_desc_batch_download(self.mgr._h, self.ptr, _p(descs), _p(off)))
+        return descs, off
+
+    def free(self):
+        if self.ptr:
+            lib().sgtd_desc_batch_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        self.free()
+
+
+class SearchResult:
+    def __init__(self, mgr, ptr):
+        self.mgr, self.ptr = mgr, ptr
+        self.nq = int(lib().sgtd_result_queries(ptr))
+        self.k = mgr.cfg.candidate_num
+
+    def download(self):
+        loops = np.zeros(self.nq, LOOP_DTYPE)
+        cands = np.zeros(self.nq * self.k, CAND_DTYPE)
+        self.mgr._chk(lib().sgtd_result_download(self.mgr._h, self.ptr, _p(loops), _p(cands)))
+        return loops, cands.reshape(self.nq, self.k)
+
+    def download_loops(self):
+        loops = np.zeros(self.nq, LOOP_DTYPE)
+        self.mgr._chk(lib().sgtd_result_download(self.mgr._h, self.ptr, _p(loops), None))
+        return loops
+
+    def matches(self, q, c, nmatch):
+        m_q = np.zeros(nmatch, np.int32)
+        m_cell = np.zeros(nmatch, np.uint8)
+        m_g = np.zeros(nmatch, np.uint32)
+        self.mgr._chk(lib().sgtd_result_matches(self.mgr._h, self.ptr, q, c, _p(m_q), _p(m_cell), _p(m_g), nmatch))
+        return m_q, m_cell, m_g
+
+    def inliers(self, q, c, ninlier):
+        inl = np.zeros(max(ninlier, 1), np.int32)
+        self.mgr._chk(lib().sgtd_result_inliers(self.mgr._h, self.ptr, q, c, _p(inl), ninlier))
+        return inl[:ninlier]
+
+    def votes(self, q, n_frames):
+        v = np.zeros(max(n_frames, 1), np.int32)
+        self.mgr._chk(lib().sgtd_result_votes(self.mgr._h, self.ptr, q, _p(v), n_frames))
+        return v[:n_frames]
+
+    def stats(self):
+        s, t = VoteStats(), Timings()
+        self.mgr._chk(lib().sgtd_result_stats(self.mgr._h, self.ptr, C.byref(s), C.byref(t)))
+        return ({k: getattr(s, k) for k in ("Q", "P", "Pfound", "E", "M")},
+                {k: getattr(t, k) for k, _ in Timings._fields_})
+
+    def free(self):
+        if self.ptr:
+            lib().sgtd_result_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        self.free()
+
+
+class STDescManager:
+    """Host-side mirror of the reference's STDescManager
+    (R/include/desc/STDesc.h:342-440) over the C ABI; batch-first."""
+
+    def __init__(self, cfg=None, device=0, **over):
+        self.cfg = cfg or default_config(**over)
+        h = C.c_void_p()
+        rc = lib().sgtd_create(C.byref(self.cfg), device, C.byref(h))
+        if rc:
+            raise SgtdError(rc, (lib().sgtd_last_error(None) or b"").decode())
+        self._h = h
+
+    def _chk(self, rc):
+        if rc:
+            raise SgtdError(rc, (lib().sgtd_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sgtd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def current_frame_id_(self):
+        return int(lib().sgtd_current_frame_id(self._h))
+
+    @property
+    def db_size(self):
+        return int(lib().sgtd_db_size(self._h))
+
+    @property
+    def kernel_launches(self):
+        return int(lib().sgtd_kernel_launches(self._h))
+
+    @property
+    def stream(self):
+        return int(lib().sgtd_stream(self._h) or 0)
+
+    def shard_init(self, rank, nranks, frames_per_rank, unique_id=None):
+        self._chk(lib().sgtd_shard_init(self._h, rank, nranks, frames_per_rank, _p(unique_id)))
+
+    # -- BuildSingleScanSTD, batched -------------------------------------------------------
+    def build(self, nodes, offsets=None, frame_ids=None, nscans=None):
+        """nodes: NODE_DTYPE array (host) or raw device pointer; offsets int64 [nscans+1]."""
+        if isinstance(nodes, np.ndarray):
+            nodes = np.ascontiguousarray(nodes, NODE_DTYPE)
+            if offsets is None:
+                offsets = np.array([0, nodes.shape[0]], np.int64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        ns = offsets.shape[0] - 1 if nscans is None else nscans
+        if frame_ids is not None:
+            frame_ids = np.ascontiguousarray(frame_ids, np.uint32)
+        out = C.c_void_p()
+        self._chk(lib().sgtd_build_descriptors(self._h, _p(nodes), _p(offsets), ns, _p(frame_ids), C.byref(out)))
+        return DescBatch(self, out)
+
+    def upload(self, descs, offsets=None):
+        descs = np.ascontiguousarray(descs, DESC_DTYPE)
+        if offsets is None:
+            offsets = np.array([0, descs.shape[0]], np.int64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        out = C.c_void_p()
+        self._chk(lib().sgtd_desc_batch_upload(self._h, _p(descs), _p(offsets), offsets.shape[0] - 1, C.byref(out)))
+        return DescBatch(self, out)
+
+    # -- AddSTDescs ---------------------------------------------------------------------------
+    def add(self, batch):
+        self._chk(lib().sgtd_add_descriptors(self._h, batch.ptr))
+
+    def reserve(self, n_desc, n_frames):
+        self._chk(lib().sgtd_reserve(self._h, n_desc, n_frames))
+
+    def finalize(self):
+        self._chk(lib().sgtd_finalize_db(self._h))
+
+    # -- SearchLoop, batched ------------------------------------------------------------------
+    def search(self, batch):
+        out = C.c_void_p()
+        self._chk(lib().sgtd_search(self._h, batch.ptr, C.byref(out)))
+        return SearchResult(self, out)
+
+    def db_fetch(self, g):
+        g = np.ascontiguousarray(g, np.uint32)
+        out = np.zeros(g.shape[0], DESC_DTYPE)
+        self._chk(lib().sgtd_db_fetch(self._h, _p(g), g.shape[0], _p(out)))
+        return out
+
+    def synchronize(self):
+        self._chk(lib().sgtd_synchronize(self._h))
+
+
+def nccl_unique_id():
+    buf = np.zeros(128, np.uint8)
+    rc = lib().sgtd_nccl_unique_id(_p(buf))
+    if rc:
+        raise SgtdError(rc, "sgtd_nccl_unique_id")
+    return buf
+
+
+def make_nodes(xyz, label):
+    xyz = np.asarray(xyz, np.float32).reshape(-1, 3)
+    out = np.zeros(xyz.shape[0], NODE_DTYPE)
+    out["x"], out["y"], out["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    out["label"] = np.asarray(label, np.uint32)
+    return out

@@ -1,0 +1,840 @@
+// search.cu -- stages 3b + 4: query voting, top-k, match lists, verification.
+//
+// Replaces STDescManager::SearchLoop (R/src/STDesc.cpp:84-147):
+//   k_vote      candidate_selector's probe loop + vote array  (:351-420)
+//   k_topk      the candidate_num x argmax ranking            (:423-433)
+//   k_merge     (multi-shard) deterministic merge of per-shard top-k lists
+//   k_collect   match_triangle_list of each selected keyframe (:437-447)
+//   k_verify    candidate_verify + triangle_solver            (:462-571)
+//   k_best      best-candidate selection / icp_threshold      (:103-146)
+//
+// All FP64 comparisons are the reference's, reformulated without changing any
+// outcome: "sqrt(x) < t" is evaluated as "x < sq_threshold(t)".
+#include <cub/device/device_scan.cuh>
+#include <nccl.h>
+
+#include "internal.cuh"
+
+namespace sgtd {
+
+// ============================ vote kernel =======================================
+struct VoteParams {
+  const DescRec *q;        // query descriptors of the whole batch
+  const int64_t *q_off;    // nq+1
+  int nq;
+  int64_t nd;              // total query descriptors
+  const Bucket *table;
+  uint64_t mask;
+  const double *s0, *s1, *s2;
+  const uint32_t *fr;      // local frame per entry
+  uint32_t frame_lo;
+  int64_t F;               // local frames
+  double rough;
+  uint32_t *votes;         // nq * F
+  unsigned long long *counters;  // Q,P,Pfound,E,M
+};
+
+__device__ __forceinline__ double norm3(double x, double y, double z) {
+  return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+}
+__device__ __forceinline__ double sqn3(double x, double y, double z) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+}
+
+// probe `ord` (0..26, x outermost) of a query descriptor: the STDesc_LOC it
+// addresses and whether it passes the 1.5-ball test (STDesc.cpp:358-369).
+__device__ __forceinline__ bool probe_key(const DescRec &r, int ord, uint64_t &key) {
+  const int ix = ord / 9 - 1, iy = (ord / 3) % 3 - 1, iz = ord % 3 - 1;
+  const int px = __double2int_rz(__dadd_rn(r.s[0], (double)ix));  // (int)(side + inc): toward zero
+  const int py = __double2int_rz(__dadd_rn(r.s[1], (double)iy));
+  const int pz = __double2int_rz(__dadd_rn(r.s[2], (double)iz));
+  const double cx = __dadd_rn((double)px, 0.5), cy = __dadd_rn((double)py, 0.5), cz = __dadd_rn((double)pz, 0.5);
+  const bool in_ball = norm3(__dsub_rn(r.s[0], cx), __dsub_rn(r.s[1], cy), __dsub_rn(r.s[2], cz)) < 1.5;
+  key = pack_key((uint32_t)px, (uint32_t)py, (uint32_t)pz, r.code);
+  return in_ball && px >= 0 && py >= 0 && pz >= 0;
+}
+
+__device__ __forceinline__ bool table_find(const Bucket *table, uint64_t mask, uint64_t key, uint32_t &off,
+                                           uint32_t &cnt) {
+  uint64_t pos = mix64(key) & mask;
+  while (true) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&table[pos]));
+    const uint64_t k = ((uint64_t)raw.y << 32) | raw.x;
+    if (k == key) { off = raw.z; cnt = raw.w; return true; }
+    if (k == SGTD_EMPTY_KEY) return false;
+    pos = (pos + 1) & mask;
+  }
+}
+
+constexpr int kVoteThreads = 256;
+
+// One warp per query descriptor (persistent, strided).  Lanes 0..26 evaluate the
+// 27 probes and look their bucket up; the warp then streams every found bucket
+// with coalesced SoA loads (8 B x 3 + 4 B per entry) and votes with fire-and-
+// forget reductions (RED.ADD) into the query's per-keyframe counter row.
+__global__ void __launch_bounds__(kVoteThreads) k_vote(VoteParams P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * kVoteThreads + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * kVoteThreads) >> 5;
+  unsigned long long cP = 0, cPf = 0, cE = 0, cM = 0, cQ = 0;
+  int qi = 0;
+  for (int64_t d = warp; d < P.nd; d += nwarps) {
+    // query index of descriptor d (uniform binary search over q_off)
+    if (!(d >= P.q_off[qi] && d < P.q_off[qi + 1])) {
+      int lo = 0, hi = P.nq - 1;
+      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (P.q_off[mid] <= d) lo = mid; else hi = mid - 1; }
+      qi = lo;
+    }
+    const DescRec r = P.q[d];
+    const double thr = __dmul_rn(norm3(r.s[0], r.s[1], r.s[2]), P.rough);
+    const double thr2 = sq_threshold(thr);
+    uint32_t off = 0, cnt = 0;
+    bool pass = false;
+    if (lane < 27) {
+      uint64_t key;
+      pass = probe_key(r, lane, key);
+      if (pass && !table_find(P.table, P.mask, key, off, cnt)) cnt = 0;
+    }
+    const unsigned m_pass = __ballot_sync(0xffffffffu, pass);
+    unsigned m_found = __ballot_sync(0xffffffffu, cnt > 0);
+    cQ += 1; cP += __popc(m_pass); cPf += __popc(m_found);
+    uint32_t *row = P.votes + (size_t)qi * (size_t)P.F;
+    while (m_found) {
+      const int src = __ffs(m_found) - 1;
+      m_found &= m_found - 1;
+      const uint32_t o = __shfl_sync(0xffffffffu, off, src);
+      const uint32_t n = __shfl_sync(0xffffffffu, cnt, src);
+      cE += n;
+      for (uint32_t e0 = 0; e0 < n; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        bool hit = false;
+        uint32_t f = 0;
+        if (e < n) {
+          const size_t idx = (size_t)o + e;
+          const double a = __ldg(P.s0 + idx), b = __ldg(P.s1 + idx), c = __ldg(P.s2 + idx);
+          f = __ldg(P.fr + idx);
+          const double d2 = sqn3(__dsub_rn(r.s[0], a), __dsub_rn(r.s[1], b), __dsub_rn(r.s[2], c));
+          // (src.frame_id_ - db.frame_id_) > 0 on unsigned == "!=" (STDesc.cpp:373)
+          hit = (f + P.frame_lo != r.frame) && (d2 < thr2);
+        }
+        if (hit) atomicAdd(row + f, 1u);
+        cM += __popc(__ballot_sync(0xffffffffu, hit));
+      }
+    }
+  }
+  if (lane == 0 && P.counters) {
+    atomicAdd(P.counters + 0, cQ); atomicAdd(P.counters + 1, cP); atomicAdd(P.counters + 2, cPf);
+    atomicAdd(P.counters + 3, cE);
+  }
+  if (lane == 0 && P.counters) atomicAdd(P.counters + 4, cM);
+}
+
+// ============================ top-k ==============================================
+constexpr int kTopkThreads = 256;
+constexpr int kMaxCand = 256;
+
+__device__ __forceinline__ unsigned long long composite(uint32_t votes, uint32_t frame) {
+  // larger == better: more votes, then LOWER frame id (first index of the maximum, :426-431)
+  return ((unsigned long long)votes << 32) | (unsigned long long)(0xFFFFFFFFu - frame);
+}
+
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T *s_tmp) {
+  // 256-thread block reduction, result broadcast
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T t = 0;
+#pragma unroll
+  for (int w = 0; w < kTopkThreads / 32; ++w) t += s_tmp[w];
+  return t;
+}
+
+// One CTA per query: exact selection of the k best keyframes by (votes desc,
+// frame asc) among those with >= 5 votes.  Radix-select on the 32-bit vote
+// value (3 histogram passes over the row) finds the k-th largest value T; all
+// rows > T are taken, ties at T are taken in ascending frame order.
+__global__ void __launch_bounds__(kTopkThreads) k_topk(const uint32_t *votes, int64_t F, uint32_t frame_lo, int k,
+                                                       int32_t *out_votes, int32_t *out_frames) {
+  __shared__ uint32_t s_hist[2048];
+  __shared__ unsigned long long s_list[kMaxCand];
+  __shared__ uint32_t s_scan[kTopkThreads];
+  __shared__ uint32_t s_tmp[kTopkThreads / 32];
+  __shared__ uint32_t s_prefix, s_mask, s_need, s_nlist;
+  const int tid = threadIdx.x;
+  const int q = blockIdx.x;
+  const uint32_t *row = votes + (size_t)q * (size_t)F;
+  // pass A: how many keyframes have >= 5 votes
+  uint32_t n5 = 0;
+  for (int64_t f = tid; f < F; f += kTopkThreads) n5 += row[f] >= 5u;
+  n5 = block_sum<uint32_t>(n5, s_tmp);
+  uint32_t T, r;  // take v > T, plus the first r (frame asc) with v == T
+  if (n5 <= (uint32_t)k) { T = 4; r = 0; }
+  else {
+    if (tid == 0) { s_prefix = 0; s_mask = 0; s_need = (uint32_t)k; }
+    const int shifts[3] = {22, 11, 0};
+    const int widths[3] = {10, 11, 11};
+    for (int p = 0; p < 3; ++p) {
+      for (int i = tid; i < 2048; i += kTopkThreads) s_hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix, mask = s_mask;
+      const uint32_t dmask = (1u << widths[p]) - 1u;
+      for (int64_t f = tid; f < F; f += kTopkThreads) {
+        const uint32_t v = row[f];
+        if ((v & mask) == prefix) atomicAdd(&s_hist[(v >> shifts[p]) & dmask], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t need = s_need;
+        int b = (int)dmask;
+        for (; b > 0; --b) { if (s_hist[b] >= need) break; need -= s_hist[b]; }
+        s_need = need;
+        s_prefix = prefix | ((uint32_t)b << shifts[p]);
+        s_mask = mask | (dmask << shifts[p]);
+      }
+      __syncthreads();
+    }
+    T = s_prefix; r = s_need;  // r of the entries equal to T are still needed
+  }
+  if (tid == 0) s_nlist = 0;
+  __syncthreads();
+  // pass C: everything above T (any order), then ties at T in frame order
+  for (int64_t f = tid; f < F; f += kTopkThreads) {
+    const uint32_t v = row[f];
+    if (v > T) { uint32_t p = atomicAdd(&s_nlist, 1u); if (p < kMaxCand) s_list[p] = composite(v, (uint32_t)f + frame_lo); }
+  }
+  __syncthreads();
+  if (r > 0) {
+    const int64_t chunk = (F + kTopkThreads - 1) / kTopkThreads;
+    const int64_t f0 = (int64_t)tid * chunk, f1 = min(F, f0 + chunk);
+    uint32_t mine = 0;
+    for (int64_t f = f0; f < f1; ++f) mine += row[f] == T;
+    s_scan[tid] = mine;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int t = 0; t < tid; ++t) before += s_scan[t];
+    const uint32_t base = s_nlist;
+    __syncthreads();
+    for (int64_t f = f0; f < f1 && before < r; ++f)
+      if (row[f] == T) { s_list[base + before] = composite(T, (uint32_t)f + frame_lo); ++before; }
+    __syncthreads();
+    if (tid == 0) s_nlist = base + r;
+    __syncthreads();
+  }
+  const int m = (int)min(s_nlist, (uint32_t)k);
+  // rank sort (m <= k <= 256): composites are distinct (distinct frames)
+  for (int i = tid; i < k; i += kTopkThreads) {
+    if (i < m) {
+      const unsigned long long me = s_list[i];
+      int rank = 0;
+      for (int j = 0; j < m; ++j) rank += s_list[j] > me;
+      out_votes[(size_t)q * k + rank] = (int32_t)(me >> 32);
+      out_frames[(size_t)q * k + rank] = (int32_t)(0xFFFFFFFFu - (uint32_t)(me & 0xFFFFFFFFu));
+    }
+  }
+  for (int i = m + tid; i < k; i += kTopkThreads) { out_votes[(size_t)q * k + i] = 0; out_frames[(size_t)q * k + i] = -1; }
+}
+
+// Deterministic merge of nlists top-k lists: k best by (votes desc, frame asc).
+// Shared by the device kernel and sgtd_merge_topk_host.
+__host__ __device__ inline void merge_rank(const int32_t *votes, const int32_t *frames, int total, int i, int k,
+                                           int32_t *out_votes, int32_t *out_frames) {
+  const int32_t v = votes[i], f = frames[i];
+  if (v <= 0) return;
+  int rank = 0;
+  for (int j = 0; j < total; ++j) {
+    const int32_t vj = votes[j], fj = frames[j];
+    if (vj <= 0) continue;
+    rank += (vj > v) || (vj == v && fj < f);
+  }
+  if (rank < k) { out_votes[rank] = v; out_frames[rank] = f; }
+}
+
+void merge_topk_host(const int32_t *votes, const int32_t *frames, int nlists, int k, int32_t *out_votes,
+                     int32_t *out_frames) {
+  for (int i = 0; i < k; ++i) { out_votes[i] = 0; out_frames[i] = -1; }
+  for (int i = 0; i < nlists * k; ++i) merge_rank(votes, frames, nlists * k, i, k, out_votes, out_frames);
+}
+
+// gathered: [nranks][nq][k] ; out: [nq][k]
+__global__ void k_merge(const int32_t *g_votes, const int32_t *g_frames, int nranks, int nq, int k,
+                        int32_t *out_votes, int32_t *out_frames) {
+  extern __shared__ int32_t s_m[];
+  int32_t *sv = s_m, *sf = s_m + nranks * k;
+  const int q = blockIdx.x;
+  for (int i = threadIdx.x; i < nranks * k; i += blockDim.x) {
+    const int rk = i / k, c = i - rk * k;
+    sv[i] = g_votes[((size_t)rk * nq + q) * k + c];
+    sf[i] = g_frames[((size_t)rk * nq + q) * k + c];
+  }
+  for (int i = threadIdx.x; i < k; i += blockDim.x) { out_votes[(size_t)q * k + i] = 0; out_frames[(size_t)q * k + i] = -1; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nranks * k; i += blockDim.x)
+    merge_rank(sv, sf, nranks * k, i, k, out_votes + (size_t)q * k, out_frames + (size_t)q * k);
+}
+
+// candidates + per-slot match counts (owned slots only)
+__global__ void k_init_cands(const int32_t *t_votes, const int32_t *t_frames, int n, int64_t frame_lo, int64_t F,
+                             sgtd_candidate *cands, int64_t *cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sgtd_candidate c;
+  memset(&c, 0, sizeof(c));
+  c.frame = t_frames[i]; c.votes = t_votes[i]; c.nmatch = t_votes[i];
+  c.score = -1; c.best_hyp = -1; c.match_off = -1; c.inlier_off = -1;
+  c.R[0] = c.R[4] = c.R[8] = 1.0;
+  const bool owned = c.votes > 0 && c.frame >= frame_lo && c.frame < frame_lo + F;
+  cnt[i] = owned ? c.votes : 0;
+  if (c.votes <= 0) { c.frame = -1; c.nmatch = 0; }
+  cands[i] = c;
+}
+__global__ void k_set_offsets(sgtd_candidate *cands, const int64_t *cnt, const int64_t *off, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (cnt[i] > 0) { cands[i].match_off = off[i]; cands[i].inlier_off = off[i]; }
+}
+
+// ============================ match lists ==========================================
+constexpr int kCollectThreads = 256;
+constexpr int kSmemKeys = 4096;
+
+struct CollectParams {
+  const sgtd_candidate *cands;
+  int k;
+  const DescRec *q; const int64_t *q_off;
+  const DescRec *db; const int64_t *frame_off; const uint64_t *f_key; const uint32_t *f_g;
+  int64_t frame_lo;
+  double rough;
+  uint32_t *m_q, *m_g; uint8_t *m_cell;
+};
+
+// matches of query descriptor r against keyframe view keys[0..nf): calls emit(ord, g)
+template <typename Emit>
+__device__ __forceinline__ void desc_vs_frame(const DescRec &r, const uint64_t *keys, int nf, const uint32_t *fg,
+                                              const DescRec *db, double rough, Emit emit) {
+  const double thr2 = sq_threshold(__dmul_rn(norm3(r.s[0], r.s[1], r.s[2]), rough));
+  for (int ord = 0; ord < 27; ++ord) {
+    uint64_t key;
+    if (!probe_key(r, ord, key)) continue;
+    int lo = 0, hi = nf;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    for (int p = lo; p < nf && keys[p] == key; ++p) {
+      const uint32_t g = fg[p];
+      const DescRec e = db[g];
+      if (e.frame == r.frame) continue;
+      const double d2 = sqn3(__dsub_rn(r.s[0], e.s[0]), __dsub_rn(r.s[1], e.s[1]), __dsub_rn(r.s[2], e.s[2]));
+      if (d2 < thr2) emit(ord, g);
+    }
+  }
+}
+
+// One CTA per (query, candidate keyframe): the keyframe's key-sorted view sits in
+// shared memory; each thread joins one query descriptor against it (27 binary
+// searches); a block scan turns per-descriptor counts into the reference's
+// (descriptor, probe ordinal, bucket position) order.
+__global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
+  __shared__ uint64_t s_keys[kSmemKeys];
+  __shared__ uint32_t s_warp[kCollectThreads / 32];
+  const sgtd_candidate c = P.cands[blockIdx.x];
+  if (c.match_off < 0 || c.nmatch <= 0) return;
+  const int q = blockIdx.x / P.k;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t fl = c.frame - P.frame_lo;
+  const int64_t fo = P.frame_off[fl];
+  const int nf = (int)(P.frame_off[fl + 1] - fo);
+  const uint64_t *keys = P.f_key + fo;
+  if (nf <= kSmemKeys) {
+    for (int i = tid; i < nf; i += kCollectThreads) s_keys[i] = keys[i];
+    keys = s_keys;
+  }
+  __syncthreads();
+  const uint32_t *fg = P.f_g + fo;
+  const int64_t q0 = P.q_off[q], q1 = P.q_off[q + 1];
+  int64_t base = c.match_off;
+  const int64_t limit = c.match_off + c.nmatch;
+  for (int64_t i0 = q0; i0 < q1; i0 += kCollectThreads) {
+    const int64_t i = i0 + tid;
+    uint32_t cnt = 0;
+    DescRec r;
+    if (i < q1) {
+      r = P.q[i];
+      desc_vs_frame(r, keys, nf, fg, P.db, P.rough, [&](int, uint32_t) { ++cnt; });
+    }
+    // block exclusive scan of cnt
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kCollectThreads / 32; ++w) { if (w < warp) wbase += s_warp[w]; total += s_warp[w]; }
+    if (cnt) {
+      int64_t pos = base + wbase + incl - cnt;
+      const uint32_t qi = (uint32_t)(i - q0);
+      desc_vs_frame(r, keys, nf, fg, P.db, P.rough, [&](int ord, uint32_t g) {
+        if (pos < limit) { P.m_q[pos] = qi; P.m_cell[pos] = (uint8_t)ord; P.m_g[pos] = g; }
+        ++pos;
+      });
+    }
+    base += total;
+  }
+}
+
+// ============================ verification ===========================================
+constexpr int kVerifyThreads = 64;
+
+struct Rot2 { double c, s; };
+__device__ __forceinline__ Rot2 rot_t(Rot2 j) { Rot2 r; r.c = j.c; r.s = -j.s; return r; }
+
+// rows p,q of a row-major 3x3: x' = c x + s y ; y' = -s x + c y
+__device__ __forceinline__ void rot_rows(double *M, int p, int q, Rot2 j) {
+  if (j.c == 1.0 && j.s == 0.0) return;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double xi = M[p * 3 + i], yi = M[q * 3 + i];
+    M[p * 3 + i] = __dadd_rn(__dmul_rn(j.c, xi), __dmul_rn(j.s, yi));
+    M[q * 3 + i] = __dadd_rn(__dmul_rn(-j.s, xi), __dmul_rn(j.c, yi));
+  }
+}
+__device__ __forceinline__ void rot_cols(double *M, int p, int q, Rot2 jr) {
+  const Rot2 j = rot_t(jr);
+  if (j.c == 1.0 && j.s == 0.0) return;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double xi = M[i * 3 + p], yi = M[i * 3 + q];
+    M[i * 3 + p] = __dadd_rn(__dmul_rn(j.c, xi), __dmul_rn(j.s, yi));
+    M[i * 3 + q] = __dadd_rn(__dmul_rn(-j.s, xi), __dmul_rn(j.c, yi));
+  }
+}
+
+// Two-sided Jacobi SVD of a 3x3 (the algorithm of Eigen::JacobiSVD for square
+// real input, which triangle_solver calls at STDesc.cpp:560): W = U S V^T.
+__device__ void svd3(const double *A, double *U, double *V) {
+  const double kMin = 2.2250738585072014e-308, kPrec = 2.0 * 2.220446049250313e-16;
+  double scale = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) scale = fmax(scale, fabs(A[i]));
+  if (scale == 0.0) scale = 1.0;
+  double W[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { W[i] = A[i] / scale; U[i] = V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+  double maxDiag = fmax(fabs(W[0]), fmax(fabs(W[4]), fabs(W[8])));
+  bool finished = false;
+  for (int sweep = 0; sweep < 64 && !finished; ++sweep) {
+    finished = true;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = (pq == 0) ? 1 : 2, q = (pq == 2) ? 1 : 0;  // (1,0) (2,0) (2,1)
+      const double threshold = fmax(kMin, __dmul_rn(kPrec, maxDiag));
+      if (fabs(W[p * 3 + q]) > threshold || fabs(W[q * 3 + p]) > threshold) {
+        finished = false;
+        // real_2x2_jacobi_svd
+        double m00 = W[p * 3 + p], m01 = W[p * 3 + q], m10 = W[q * 3 + p], m11 = W[q * 3 + q];
+        Rot2 rot1;
+        const double t = __dadd_rn(m00, m11), d = __dsub_rn(m10, m01);
+        if (fabs(d) < kMin) { rot1.s = 0.0; rot1.c = 1.0; }
+        else {
+          const double u = t / d;
+          const double tmp = __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(u, u)));
+          rot1.s = 1.0 / tmp; rot1.c = u / tmp;
+        }
+        if (!(rot1.c == 1.0 && rot1.s == 0.0)) {
+          const double a0 = __dadd_rn(__dmul_rn(rot1.c, m00), __dmul_rn(rot1.s, m10));
+          const double a1 = __dadd_rn(__dmul_rn(rot1.c, m01), __dmul_rn(rot1.s, m11));
+          const double b0 = __dadd_rn(__dmul_rn(-rot1.s, m00), __dmul_rn(rot1.c, m10));
+          const double b1 = __dadd_rn(__dmul_rn(-rot1.s, m01), __dmul_rn(rot1.c, m11));
+          m00 = a0; m01 = a1; m10 = b0; m11 = b1;
+        }
+        (void)m10;
+        // makeJacobi(m00, m01, m11)
+        Rot2 jr;
+        const double deno = __dmul_rn(2.0, fabs(m01));
+        if (deno < kMin) { jr.c = 1.0; jr.s = 0.0; }
+        else {
+          const double tau = __dsub_rn(m00, m11) / deno;
+          const double w = __dsqrt_rn(__dadd_rn(__dmul_rn(tau, tau), 1.0));
+          const double tt = (tau > 0.0) ? 1.0 / __dadd_rn(tau, w) : 1.0 / __dsub_rn(tau, w);
+          const double sign_t = tt > 0.0 ? 1.0 : -1.0;
+          const double n = 1.0 / __dsqrt_rn(__dadd_rn(__dmul_rn(tt, tt), 1.0));
+          jr.s = __dmul_rn(__dmul_rn(__dmul_rn(-sign_t, m01 / fabs(m01)), fabs(tt)), n);
+          jr.c = n;
+        }
+        // j_left = rot1 * j_right^T
+        const Rot2 jrt = rot_t(jr);
+        Rot2 jl;
+        jl.c = __dsub_rn(__dmul_rn(rot1.c, jrt.c), __dmul_rn(rot1.s, jrt.s));
+        jl.s = __dadd_rn(__dmul_rn(rot1.c, jrt.s), __dmul_rn(rot1.s, jrt.c));
+        rot_rows(W, p, q, jl);
+        rot_cols(U, p, q, rot_t(jl));
+        rot_cols(W, p, q, jr);
+        rot_cols(V, p, q, jr);
+        maxDiag = fmax(maxDiag, fmax(fabs(W[p * 3 + p]), fabs(W[q * 3 + q])));
+      }
+    }
+  }
+  double sv[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double a = fabs(W[i * 3 + i]);
+    sv[i] = a;
+    if (a != 0.0) { const double f = W[i * 3 + i] / a; U[0 * 3 + i] *= f; U[1 * 3 + i] *= f; U[2 * 3 + i] *= f; }
+  }
+  // sort singular values descending (selection, swapping columns of U and V)
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int pos = i; double mx = sv[i];
+#pragma unroll
+    for (int kk = i + 1; kk < 3; ++kk) if (sv[kk] > mx) { mx = sv[kk]; pos = kk; }
+    if (mx == 0.0) break;
+    if (pos != i) {
+      double t = sv[i]; sv[i] = sv[pos]; sv[pos] = t;
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        t = U[rr * 3 + i]; U[rr * 3 + i] = U[rr * 3 + pos]; U[rr * 3 + pos] = t;
+        t = V[rr * 3 + i]; V[rr * 3 + i] = V[rr * 3 + pos]; V[rr * 3 + pos] = t;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ double dot3s(double a0, double b0, double a1, double b1, double a2, double b2) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+}
+
+// triangle_solver (STDesc.cpp:549-571).  sv/rv: 9 floats A,B,C of source / reference.
+__device__ void kabsch3(const float *svf, const float *rvf, double *R, double *t) {
+  double sv[9], rv[9], sc[3], rc[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { sv[i] = (double)svf[i]; rv[i] = (double)rvf[i]; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    sc[k] = __dadd_rn(__dadd_rn(sv[k], sv[3 + k]), sv[6 + k]) / 3.0;  // center_ = (A+B+C)/3
+    rc[k] = __dadd_rn(__dadd_rn(rv[k], rv[3 + k]), rv[6 + k]) / 3.0;
+  }
+  double src[9], ref[9];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      src[k * 3 + c] = __dsub_rn(sv[c * 3 + k], sc[k]);
+      ref[k * 3 + c] = __dsub_rn(rv[c * 3 + k], rc[k]);
+    }
+  double cov[9], U[9], V[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      cov[i * 3 + j] = dot3s(src[i * 3], ref[j * 3], src[i * 3 + 1], ref[j * 3 + 1], src[i * 3 + 2], ref[j * 3 + 2]);
+  svd3(cov, U, V);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      R[i * 3 + j] = dot3s(V[i * 3], U[j * 3], V[i * 3 + 1], U[j * 3 + 1], V[i * 3 + 2], U[j * 3 + 2]);
+  const double det = __dadd_rn(__dsub_rn(__dmul_rn(R[0], __dsub_rn(__dmul_rn(R[4], R[8]), __dmul_rn(R[5], R[7]))),
+                                         __dmul_rn(R[1], __dsub_rn(__dmul_rn(R[3], R[8]), __dmul_rn(R[5], R[6])))),
+                               __dmul_rn(R[2], __dsub_rn(__dmul_rn(R[3], R[7]), __dmul_rn(R[4], R[6]))));
+  if (det < 0.0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        R[i * 3 + j] = dot3s(V[i * 3], U[j * 3], V[i * 3 + 1], U[j * 3 + 1], -V[i * 3 + 2], U[j * 3 + 2]);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    t[i] = __dadd_rn(dot3s(-R[i * 3], sc[0], -R[i * 3 + 1], sc[1], -R[i * 3 + 2], sc[2]), rc[i]);
+}
+
+// all three vertex residuals < 3.0 m (STDesc.cpp:487-501); sqrt(x) < 3  <=>  x < 9 exactly
+__device__ __forceinline__ bool pair_inlier(const double *R, const double *t, const float *a, const float *b) {
+  bool ok = true;
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    const double px = (double)a[v * 3], py = (double)a[v * 3 + 1], pz = (double)a[v * 3 + 2];
+    const double dx = __dsub_rn(__dadd_rn(dot3s(R[0], px, R[1], py, R[2], pz), t[0]), (double)b[v * 3]);
+    const double dy = __dsub_rn(__dadd_rn(dot3s(R[3], px, R[4], py, R[5], pz), t[1]), (double)b[v * 3 + 1]);
+    const double dz = __dsub_rn(__dadd_rn(dot3s(R[6], px, R[7], py, R[8], pz), t[2]), (double)b[v * 3 + 2]);
+    ok = ok && (sqn3(dx, dy, dz) < 9.0);
+  }
+  return ok;
+}
+
+struct VerifyParams {
+  sgtd_candidate *cands;
+  int k;
+  const DescVert *qv; const int64_t *q_off;
+  const DescVert *dbv;
+  const uint32_t *m_q, *m_g;
+  int32_t *inl;
+};
+
+__device__ __forceinline__ void load_pair(const VerifyParams &P, int64_t q0, int64_t j, float *a, float *b) {
+  const DescVert x = P.qv[q0 + P.m_q[j]];
+  const DescVert y = P.dbv[P.m_g[j]];
+  a[0] = x.a.x; a[1] = x.a.y; a[2] = x.a.z; a[3] = x.b.x; a[4] = x.b.y; a[5] = x.b.z; a[6] = x.c.x; a[7] = x.c.y; a[8] = x.c.z;
+  b[0] = y.a.x; b[1] = y.a.y; b[2] = y.a.z; b[3] = y.b.x; b[4] = y.b.y; b[5] = y.b.z; b[6] = y.c.x; b[7] = y.c.y; b[8] = y.c.z;
+}
+
+// One CTA (2 warps) per candidate.  Thread h owns hypothesis h (<= 50): it solves
+// the 3-point Kabsch of pair h*skip and keeps (R,t) in registers.  Match pairs
+// are staged 64 at a time in shared memory; every hypothesis thread walks the
+// tile with broadcast reads, so each pair is fetched from HBM/L2 once per pass.
+__global__ void __launch_bounds__(kVerifyThreads) k_verify(VerifyParams P) {
+  __shared__ float s_a[kVerifyThreads][9];
+  __shared__ float s_b[kVerifyThreads][9];
+  __shared__ int s_vote[kVerifyThreads];
+  __shared__ double s_pose[12];
+  __shared__ int s_best, s_wcnt[2];
+  sgtd_candidate *cd = P.cands + blockIdx.x;
+  const int64_t moff = cd->match_off;
+  const int M = cd->nmatch;
+  if (moff < 0 || M <= 0) return;
+  const int q = blockIdx.x / P.k;
+  const int64_t q0 = P.q_off[q];
+  const int tid = threadIdx.x;
+  const int skip = M / 50 + 1;
+  const int H = M / skip;
+  double R[9], t[3];
+  if (tid < H) {
+    float a[9], b[9];
+    load_pair(P, q0, moff + (int64_t)tid * skip, a, b);
+    kabsch3(a, b, R, t);
+  }
+  int vote = 0;
+  for (int jb = 0; jb < M; jb += kVerifyThreads) {
+    const int nt = min(kVerifyThreads, M - jb);
+    __syncthreads();
+    if (tid < nt) load_pair(P, q0, moff + jb + tid, s_a[tid], s_b[tid]);
+    __syncthreads();
+    if (tid < H)
+      for (int jj = 0; jj < nt; ++jj) vote += pair_inlier(R, t, s_a[jj], s_b[jj]);
+  }
+  s_vote[tid] = (tid < H) ? vote : -1;
+  __syncthreads();
+  if (tid == 0) {
+    int best = 0, mv = 0;
+    for (int hh = 0; hh < H; ++hh) if (mv < s_vote[hh]) { best = hh; mv = s_vote[hh]; }
+    s_best = (mv >= 4) ? best : -1;
+  }
+  __syncthreads();
+  const int best = s_best;
+  if (best < 0) { if (tid == 0) { cd->score = -1; cd->best_hyp = -1; cd->ninlier = 0; } return; }
+  if (tid == best) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s_pose[i] = R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s_pose[9 + i] = t[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = s_pose[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t[i] = s_pose[9 + i];
+  int ninl = 0;
+  for (int jb = 0; jb < M; jb += kVerifyThreads) {
+    const int j = jb + tid;
+    bool ok = false;
+    if (j < M) {
+      float a[9], b[9];
+      load_pair(P, q0, moff + j, a, b);
+      ok = pair_inlier(R, t, a, b);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    __syncthreads();
+    if ((tid & 31) == 0) s_wcnt[tid >> 5] = __popc(bal);
+    __syncthreads();
+    const int before = ((tid >> 5) ? s_wcnt[0] : 0) + __popc(bal & ((1u << (tid & 31)) - 1u));
+    if (ok) P.inl[moff + ninl + before] = j;
+    ninl += s_wcnt[0] + s_wcnt[1];
+  }
+  if (tid == 0) {
+    cd->score = ninl; cd->ninlier = ninl; cd->best_hyp = best;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cd->R[i] = R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cd->t[i] = t[i];
+  }
+}
+
+// multi-shard: take each slot's record from the rank that owns the keyframe
+__global__ void k_pick_owner(const sgtd_candidate *gathered, int nranks, int rank, int n, int64_t frames_per_rank,
+                             sgtd_candidate *cands) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int f = cands[i].frame;
+  if (f < 0) return;
+  int owner = (int)(f / frames_per_rank);
+  if (owner >= nranks) owner = nranks - 1;
+  if (owner == rank) return;  // own record (with this rank's match/inlier offsets) stays
+  sgtd_candidate c = gathered[(size_t)owner * n + i];
+  c.match_off = -1; c.inlier_off = -1;  // lists live on the owner
+  cands[i] = c;
+}
+
+// SearchLoop tail (STDesc.cpp:103-146): first strict maximum of the scores.
+__global__ void k_best(const sgtd_candidate *cands, int nq, int k, double icp, sgtd_loop_result *loops) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  double best_score = 0.0; int best_id = -1, nc = 0;
+  for (int c = 0; c < k; ++c) {
+    const sgtd_candidate &cd = cands[(size_t)q * k + c];
+    if (cd.frame < 0) break;
+    ++nc;
+    if ((double)cd.score > best_score) { best_score = (double)cd.score; best_id = cd.frame; }
+  }
+  sgtd_loop_result r;
+  r.ncand = nc;
+  if (best_score > icp) { r.frame = best_id; r.score = best_score; } else { r.frame = -1; r.score = 0.0; }
+  loops[q] = r;
+}
+
+// ============================ host driver ================================================
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
+  cudaStream_t st = h->stream;
+  int rc = finalize_db(h);
+  if (rc) return rc;
+  const int nq = qb->nscans, k = h->c.cand_num;
+  if (k < 1 || k > kMaxCand) SGTD_FAIL(h, SGTD_E_INVALID, "candidate_num must be in [1,256]");
+  const int64_t F = h->frames_local();
+  const int64_t Fa = std::max<int64_t>(F, 1);
+  r->h = h; r->nq = nq; r->k = k; r->F_local = F;
+  const int64_t launches0 = h->launches;
+  cudaEvent_t ev[7];
+  for (auto &e : ev) SGTD_CUDA(h, cudaEventCreate(&e));
+  SGTD_CUDA(h, r->votes.reserve((size_t)nq * Fa, st, false)); r->votes.n = (size_t)nq * Fa;
+  SGTD_CUDA(h, r->cands.reserve((size_t)nq * k, st, false)); r->cands.n = (size_t)nq * k;
+  SGTD_CUDA(h, r->loops.reserve((size_t)std::max(nq, 1), st, false)); r->loops.n = nq;
+  SGTD_CUDA(h, r->counters.reserve(8, st, false));
+  // scratch: local top-k, gathered top-k, merged top-k, counts, offsets, cub temp, gathered cands
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t nslot = (size_t)nq * k;
+  size_t cubb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cubb, (int64_t *)nullptr, (int64_t *)nullptr, (int)nslot + 1, st);
+  size_t o = 0;
+  size_t o_lv = o; o += al(nslot * 4);
+  size_t o_lf = o; o += al(nslot * 4);
+  size_t o_gv = o; o += al(nslot * 4 * h->nranks);
+  size_t o_gf = o; o += al(nslot * 4 * h->nranks);
+  size_t o_mv = o; o += al(nslot * 4);
+  size_t o_mf = o; o += al(nslot * 4);
+  size_t o_cnt = o; o += al((nslot + 1) * 8);
+  size_t o_off = o; o += al((nslot + 1) * 8);
+  size_t o_cub = o; o += al(cubb);
+  size_t o_gc = o; o += (h->nranks > 1) ? al(nslot * sizeof(sgtd_candidate) * h->nranks) : 0;
+  SGTD_CUDA(h, h->scratch.reserve(o, st, false));
+  unsigned char *S = h->scratch.p;
+  int32_t *lv = (int32_t *)(S + o_lv), *lf = (int32_t *)(S + o_lf), *gv = (int32_t *)(S + o_gv), *gf = (int32_t *)(S + o_gf);
+  int32_t *mv = (int32_t *)(S + o_mv), *mf = (int32_t *)(S + o_mf);
+  int64_t *cnt = (int64_t *)(S + o_cnt), *off = (int64_t *)(S + o_off);
+
+  SGTD_CUDA(h, cudaEventRecord(ev[0], st));
+  SGTD_CUDA(h, cudaMemsetAsync(r->votes.p, 0, (size_t)nq * Fa * 4, st));
+  SGTD_CUDA(h, cudaMemsetAsync(r->counters.p, 0, 8 * 8, st));
+  if (nq > 0 && qb->n > 0 && h->rec.n > 0) {
+    VoteParams V{};
+    V.q = qb->rec.p; V.q_off = qb->d_off.p; V.nq = nq; V.nd = qb->n;
+    V.table = h->table.p; V.mask = h->table_mask;
+    V.s0 = h->v_s0.p; V.s1 = h->v_s1.p; V.s2 = h->v_s2.p; V.fr = h->v_frame.p;
+    V.frame_lo = (uint32_t)h->frame_lo(); V.F = Fa; V.rough = h->c.rough;
+    V.votes = r->votes.p; V.counters = r->counters.p;
+    const int64_t warps_needed = qb->n;
+    int grid = (int)std::min<int64_t>((warps_needed * 32 + kVoteThreads - 1) / kVoteThreads, (int64_t)h->sm_count * 8);
+    k_vote<<<grid, kVoteThreads, 0, st>>>(V);
+    SGTD_LAUNCHED(h);
+    SGTD_CUDA(h, cudaGetLastError());
+  }
+  SGTD_CUDA(h, cudaEventRecord(ev[1], st));
+  const int vote_launches = (int)(h->launches - launches0);
+  if (nq > 0) {
+    k_topk<<<nq, kTopkThreads, 0, st>>>(r->votes.p, Fa, (uint32_t)h->frame_lo(), k, lv, lf);
+    SGTD_LAUNCHED(h);
+    SGTD_CUDA(h, cudaGetLastError());
+  }
+  SGTD_CUDA(h, cudaEventRecord(ev[2], st));
+  const int32_t *tv = lv, *tf = lf;
+  if (h->nranks > 1 && h->nccl && nq > 0) {
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    if (ncclAllGather(lv, gv, nslot, ncclInt32, comm, st) != ncclSuccess) SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(votes)");
+    if (ncclAllGather(lf, gf, nslot, ncclInt32, comm, st) != ncclSuccess) SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(frames)");
+    k_merge<<<nq, 128, (size_t)h->nranks * k * 8, st>>>(gv, gf, h->nranks, nq, k, mv, mf);
+    SGTD_LAUNCHED(h);
+    SGTD_CUDA(h, cudaGetLastError());
+    tv = mv; tf = mf;
+  }
+  SGTD_CUDA(h, cudaEventRecord(ev[3], st));
+  int64_t total = 0;
+  if (nq > 0) {
+    const int nb = (int)((nslot + 255) / 256);
+    k_init_cands<<<nb, 256, 0, st>>>(tv, tf, (int)nslot, h->frame_lo(), F, r->cands.p, cnt);
+    SGTD_LAUNCHED(h);
+    SGTD_CUDA(h, cudaMemsetAsync(cnt + nslot, 0, 8, st));
+    SGTD_CUDA(h, cub::DeviceScan::ExclusiveSum(S + o_cub, cubb, cnt, off, (int)nslot + 1, st));
+    SGTD_LAUNCHED(h);
+    k_set_offsets<<<nb, 256, 0, st>>>(r->cands.p, cnt, off, (int)nslot);
+    SGTD_LAUNCHED(h);
+    SGTD_CUDA(h, cudaMemcpyAsync(&total, off + nslot, 8, cudaMemcpyDeviceToHost, st));
+    SGTD_CUDA(h, cudaStreamSynchronize(st));
+  }
+  r->total_matches = total;
+  const size_t tm = (size_t)std::max<int64_t>(total, 1);
+  SGTD_CUDA(h, r->m_q.reserve(tm, st, false)); SGTD_CUDA(h, r->m_g.reserve(tm, st, false));
+  SGTD_CUDA(h, r->m_cell.reserve(tm, st, false)); SGTD_CUDA(h, r->inl.reserve(tm, st, false));
+  r->m_q.n = r->m_g.n = r->m_cell.n = r->inl.n = (size_t)total;
+  if (total > 0) {
+    CollectParams C{};
+    C.cands = r->cands.p; C.k = k; C.q = qb->rec.p; C.q_off = qb->d_off.p;
+    C.db = h->rec.p; C.frame_off = h->d_frame_off.p; C.f_key = h->f_key.p; C.f_g = h->f_g.p;
+    C.frame_lo = h->frame_lo(); C.rough = h->c.rough;
+    C.m_q = r->m_q.p; C.m_g = r->m_g.p; C.m_cell = r->m_cell.p;
+    k_collect<<<(unsigned)nslot, kCollectThreads, 0, st>>>(C);
+    SGTD_LAUNCHED(h);
+    SGTD_CUDA(h, cudaGetLastError());
+  }
+  SGTD_CUDA(h, cudaEventRecord(ev[4], st));
+  if (total > 0) {
+    VerifyParams W{};
+    W.cands = r->cands.p; W.k = k; W.qv = qb->vert.p; W.q_off = qb->d_off.p; W.dbv = h->vert.p;
+    W.m_q = r->m_q.p; W.m_g = r->m_g.p; W.inl = r->inl.p;
+    k_verify<<<(unsigned)nslot, kVerifyThreads, 0, st>>>(W);
+    SGTD_LAUNCHED(h);
+    SGTD_CUDA(h, cudaGetLastError());
+  }
+  SGTD_CUDA(h, cudaEventRecord(ev[5], st));
+  if (h->nranks > 1 && h->nccl && nq > 0) {
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    sgtd_candidate *gc = (sgtd_candidate *)(S + o_gc);
+    if (ncclAllGather(r->cands.p, gc, nslot * sizeof(sgtd_candidate), ncclUint8, comm, st) != ncclSuccess)
+      SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(candidates)");
+    // keep this rank's own offsets for owned slots: k_pick_owner copies the owner's record, which for
+    // owned slots is this rank's own record.
+    k_pick_owner<<<(int)((nslot + 255) / 256), 256, 0, st>>>(gc, h->nranks, h->rank, (int)nslot, h->frames_per_rank, r->cands.p);
+    SGTD_LAUNCHED(h);
+    SGTD_CUDA(h, cudaGetLastError());
+  }
+  if (nq > 0) {
+    k_best<<<(nq + 127) / 128, 128, 0, st>>>(r->cands.p, nq, k, h->c.icp, r->loops.p);
+    SGTD_LAUNCHED(h);
+    SGTD_CUDA(h, cudaGetLastError());
+  }
+  SGTD_CUDA(h, cudaEventRecord(ev[6], st));
+  SGTD_CUDA(h, cudaStreamSynchronize(st));
+  r->tm.vote_ms = ev_ms(ev[0], ev[1]);
+  r->tm.topk_ms = ev_ms(ev[1], ev[2]);
+  r->tm.exchange_ms = ev_ms(ev[2], ev[3]);
+  r->tm.collect_ms = ev_ms(ev[3], ev[4]);
+  r->tm.verify_ms = ev_ms(ev[4], ev[5]);
+  r->tm.total_ms = ev_ms(ev[0], ev[6]);
+  r->tm.vote_launches = vote_launches;
+  r->tm.total_launches = (int)(h->launches - launches0);
+  for (auto &e : ev) cudaEventDestroy(e);
+  return SGTD_OK;
+}
+
+}  // namespace sgtd
