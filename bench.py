@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- one-shot localization throughput (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic queries:
+  descriptor construction for every query scan (stage 2) + vote / top-k /
+  match lists / geometric verification against the keyframe database
+  (stages 3-4), i.e. BuildSingleScanSTD + SearchLoop per query
+  (R/src/semantic_graph_localization.cpp:590-602).
+
+Workload (config.workload): BASELINE.json configs[3] -- 100k-keyframe synthetic
+city DB, 1,024-query batch.  It fits one B200 (the DB is ~30 GB), so N=1 runs it
+unsharded; N>1 shards the DB by keyframe range (strong scaling: total work is
+fixed), merges per-shard top-k lists with ncclAllGather and gathers verified
+candidates back.
+
+  value     queries/s, query nodes already resident in HBM
+  e2e       queries/s through the C ABI with HOST buffers (H2D of the node
+            arrays + D2H of loop results and candidates inside the timed region)
+  roofline  vote kernel: algorithmic bytes (32Q+16P+28E+12M, counted by the
+            kernel) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle (CPU port of the reference) on a bounded sample
+
+--impl reference times the reference's CPU path (oracle port; the reference
+cannot be compiled here) on bounded samples of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "configs[3]: 100k-keyframe synthetic city DB, 1024-query batch"
+METRIC = "one-shot localization queries/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--keyframes", type=int, default=100000)
+    ap.add_argument("--queries", type=int, default=1024)
+    ap.add_argument("--cpu-keyframes", type=int, default=4096, help="DB prefix used by the CPU sample")
+    ap.add_argument("--cpu-queries", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=8192, help="keyframes per DB-build batch")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(st):
+    return 32 * st["Q"] + 16 * st["P"] + 28 * st["E"] + 12 * st["M"]
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_sample(args, cfg, nthreads):
+    """Oracle (CPU port of the reference) on a bounded sample: the first
+    cpu_keyframes keyframes as DB and cpu_queries queries whose true place lies
+    inside that prefix.  Returns (queries/s, description)."""
+    from oracle import orc
+    xyz, lab, off = cfg["db"]
+    qx, ql, qo = cfg["queries"]
+    nkf = min(args.cpu_keyframes, off.shape[0] - 1)
+    o = orc.Oracle()
+    t0 = time.time()
+    for f in range(nkf):
+        o.add(o.build(xyz[off[f]:off[f + 1]], lab[off[f]:off[f + 1]]))
+    t_build = time.time() - t0
+    inside = np.nonzero(cfg["gt"] < nkf)[0]
+    pick = inside[:args.cpu_queries] if inside.size >= args.cpu_queries else np.arange(args.cpu_queries)
+    return o, pick, nkf, t_build
+
+
+def cpu_run(o, cfg, pick, nthreads):
+    qx, ql, qo = cfg["queries"]
+    t0 = time.time()
+    for q in pick:
+        qd = o.build(qx[qo[q]:qo[q + 1]], ql[qo[q]:qo[q + 1]])   # BuildSingleScanSTD
+        o.search(qd, nthreads=nthreads, want_votes=False)        # SearchLoop
+    return len(pick) / (time.time() - t0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from sgtd_b200 import synth
+    ncores = os.cpu_count() or 1
+    cfg = synth.make_config(3, args.keyframes, args.queries)
+    o, pick, nkf, t_build = cpu_sample(args, cfg, ncores)
+    for _ in range(args.warmup):
+        cpu_run(o, cfg, pick[:1], ncores)
+    t0 = time.time()
+    n = 0
+    for _ in range(args.steps):
+        cpu_run(o, cfg, pick, ncores)
+        n += len(pick)
+    dt = time.time() - t0
+    v = n / dt
+    sample = (f"{len(pick)} queries/step against the first {nkf} of {args.keyframes} keyframes "
+              f"(CPU cost grows with DB size, so this favours the CPU); DB build {t_build:.1f}s not timed")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "keyframes": args.keyframes, "queries": args.queries},
+            "cpu_baseline": {"value": v, "unit": "queries/s", "cores": ncores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sgtd_b200 import capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synth.make_config(3, args.keyframes, args.queries)
+    xyz, lab, off = cfg["db"]
+    qx, ql, qo = cfg["queries"]
+    nkf = off.shape[0] - 1
+    nq = qo.shape[0] - 1
+
+    mgr = capi.STDescManager(device=local)
+    fpr = (nkf + world - 1) // world
+    if world > 1:
+        uid = torch.from_numpy(capi.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+        dist.broadcast(uid, 0)
+        mgr.shard_init(rank, world, fpr, uid.cpu().numpy())
+    lo, hi = (rank * fpr, min(nkf, (rank + 1) * fpr)) if world > 1 else (0, nkf)
+
+    # ---- database build (not timed): stage 2 on the GPU for this rank's keyframes ----
+    t0 = time.time()
+    nodes = capi.make_nodes(xyz, lab)
+    for c0 in range(0, nkf, args.chunk):
+        c1 = min(nkf, c0 + args.chunk)
+        if c1 <= lo or c0 >= hi:      # not ours: advance frame ids with an empty batch
+            b = mgr.upload(np.zeros(0, capi.DESC_DTYPE), np.zeros(c1 - c0 + 1, np.int64))
+        else:
+            b = mgr.build(nodes, off[c0:c1 + 1], frame_ids=np.arange(c0, c1, dtype=np.uint32))
+        mgr.add(b)
+        b.free()
+    mgr.finalize()
+    t_db = time.time() - t0
+    assert mgr.current_frame_id_ == nkf
+
+    # ---- inputs: query nodes in HBM (value) and in pinned host memory (e2e) ----
+    qnodes = capi.make_nodes(qx, ql)
+    q_dev = torch.from_numpy(qnodes.view(np.uint8).reshape(-1)).to(dev)
+    q_pin = torch.from_numpy(qnodes.view(np.uint8).reshape(-1).copy()).pin_memory()
+    q_pin_np = q_pin.numpy().view(capi.NODE_DTYPE)
+    k = mgr.cfg.candidate_num
+    loops_pin = torch.empty(nq * capi.LOOP_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    cands_pin = torch.empty(nq * k * capi.CAND_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+
+    def step_device():
+        qb = mgr.build(q_dev.data_ptr(), qo)
+        res = mgr.search(qb)
+        out = res.stats()
+        res.free(); qb.free()                     # buffers go back to the handle's pool
+        return out
+
+    def step_e2e():
+        qb = mgr.build(q_pin_np, qo)              # H2D of the node arrays inside
+        res = mgr.search(qb)
+        capi.lib().sgtd_result_download(mgr._h, res.ptr, ctypes.c_void_p(loops_pin.data_ptr()),
+                                        ctypes.c_void_p(cands_pin.data_ptr()))   # D2H
+        out = res.stats()
+        res.free(); qb.free()
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """CUDA events on the handle's stream, barrier + synchronize on both sides."""
+        stream = torch.cuda.ExternalStream(mgr.stream, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        keep = []
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            keep.append(fn())
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, keep
+
+    for _ in range(args.warmup):
+        step_device()
+        step_e2e()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = mgr.kernel_launches
+    ms_dev, kept = timed(step_device, args.steps)
+    launches = mgr.kernel_launches - l0
+    # per-kernel numbers from the timed steps themselves (events recorded inside the library)
+    vote_ms, stats, stage = [], None, {}
+    for st, tm in kept:
+        vote_ms.append(tm["vote_ms"]); stats = st
+        for kk, vv in tm.items():
+            stage[kk] = stage.get(kk, 0.0) + vv / len(kept)
+    ms_e2e, kept = timed(step_e2e, args.steps)
+    loops = np.frombuffer(loops_pin.numpy().tobytes(), capi.LOOP_DTYPE)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:   # whole-job counters: sum over shards
+        t = torch.tensor([stats[kk] for kk in ("Q", "P", "Pfound", "E", "M")], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        tot = dict(zip(("Q", "P", "Pfound", "E", "M"), [int(x) for x in t.tolist()]))
+    else:
+        tot = stats
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        vms = float(np.mean(vote_ms))
+        ach = algorithmic_bytes(stats) / (vms * 1e-3) / 1e9      # this rank's kernel, this rank's bytes
+        found = int((loops["frame"] >= 0).sum())
+        gt = cfg["gt"]
+        # success in the reference's sense needs poses; here: best keyframe within 10 m of the true place
+        P = cfg["world"]["poses"]
+        ok = 0
+        for qi in range(nq):
+            f = loops["frame"][qi]
+            if f >= 0 and np.hypot(*(P[f, :2] - cfg["qposes"][qi, :2])) < 10.0:
+                ok += 1
+        line = {
+            "metric": METRIC, "value": nq * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "keyframes": nkf, "queries": nq, "db_descriptors": int(mgr.db_size),
+                       "sharding": f"keyframe-range x{world}", "l2": "inputs larger than L2 (DB index >> 126 MB)",
+                       "db_build_s": round(t_db, 2)},
+            "e2e": {"value": nq * args.steps / (ms_e2e * 1e-3), "unit": "queries/s",
+                    "h2d_bytes_per_step": int(qnodes.nbytes + qo.nbytes),
+                    "d2h_bytes_per_step": int(loops_pin.numel() + cands_pin.numel())},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_vote", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algorithmic_bytes(stats), "avg_launch_ms": vms,
+                         "counters": stats},
+            "stage_ms": {kk: round(vv, 3) for kk, vv in stage.items()},
+            "recall": {"found": found, "within_10m": ok, "queries": nq},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            ncores = os.cpu_count() or 1
+            o, pick, nk, tb = cpu_sample(args, cfg, ncores)
+            v = cpu_run(o, cfg, pick, ncores)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "queries/s", "cores": ncores, "kind": "port",
+                "sample": f"{len(pick)} queries against the first {nk} of {nkf} keyframes, oracle with {ncores} OpenMP threads"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    mgr.close()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -136,7 +136,9 @@ typedef struct sgtd_vote_stats {
 /* Per-stage device times of the last sgtd_search, milliseconds (CUDA events on
  * the handle's stream). */
 typedef struct sgtd_timings {
-  float vote_ms, topk_ms, exchange_ms, collect_ms, verify_ms, total_ms;
+  float clear_ms;  /* zeroing the vote rows */
+  float vote_ms;   /* the vote kernel alone */
+  float topk_ms, exchange_ms, collect_ms, verify_ms, total_ms;
   int32_t vote_launches, total_launches;
 } sgtd_timings;
 

@@ -46,7 +46,7 @@ class VoteStats(C.Structure):
 
 
 class Timings(C.Structure):
-    _fields_ = [(k, C.c_float) for k in ("vote_ms", "topk_ms", "exchange_ms", "collect_ms", "verify_ms", "total_ms")] + \
+    _fields_ = [(k, C.c_float) for k in ("clear_ms", "vote_ms", "topk_ms", "exchange_ms", "collect_ms", "verify_ms", "total_ms")] + \
                [("vote_launches", C.c_int32), ("total_launches", C.c_int32)]
 
 
@@ -183,7 +183,10 @@ class DescBatch:
             self.ptr = None
 
     def __del__(self):
-        self.free()
+        try:
+            self.free()
+        except Exception:  # interpreter shutdown
+            pass
 
 
 class SearchResult:
@@ -232,7 +235,10 @@ class SearchResult:
             self.ptr = None
 
     def __del__(self):
-        self.free()
+        try:
+            self.free()
+        except Exception:  # interpreter shutdown
+            pass
 
 
 class STDescManager:
@@ -257,7 +263,10 @@ class STDescManager:
             self._h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
 
     @property
     def current_frame_id_(self):

@@ -85,6 +85,25 @@ struct SetDevice {
 
 }  // namespace
 
+static sgtd_desc_batch *take_batch(sgtd_handle *h) {
+  sgtd_desc_batch *b;
+  if (!h->batch_pool.empty()) { b = h->batch_pool.back(); h->batch_pool.pop_back(); }
+  else b = new sgtd_desc_batch();
+  b->h = h; b->nscans = 0; b->n = 0; b->off.clear();
+  h->live_batches.insert(b);
+  return b;
+}
+static void release_batch(sgtd_desc_batch *b) { b->rec.release(); b->vert.release(); b->d_off.release(); b->h = nullptr; }
+static void release_result(sgtd_search_result *r) {
+  r->cands.release(); r->loops.release(); r->votes.release(); r->m_q.release(); r->m_g.release();
+  r->m_cell.release(); r->inl.release(); r->counters.release();
+  if (r->have_ev) for (auto &e : r->ev) cudaEventDestroy(e);
+  r->have_ev = false; r->h = nullptr;
+}
+static void destroy_batch(sgtd_desc_batch *b) { release_batch(b); delete b; }
+static void destroy_result(sgtd_search_result *r) { release_result(r); delete r; }
+constexpr size_t kPoolMax = 4;
+
 extern "C" {
 
 int sgtd_abi_version(void) { return SGTD_ABI_VERSION; }
@@ -204,7 +223,11 @@ int sgtd_destroy(sgtd_handle *h) {
   if (h->nccl) ncclCommDestroy((ncclComm_t)h->nccl);
   h->rec.release(); h->vert.release(); h->d_frame_off.release();
   h->v_s0.release(); h->v_s1.release(); h->v_s2.release(); h->v_frame.release();
-  h->table.release(); h->f_key.release(); h->f_g.release(); h->scratch.release();
+  h->table.release(); h->f_key.release(); h->f_g.release(); h->scratch.release(); h->stage_in.release();
+  for (auto *r : h->result_pool) destroy_result(r);
+  for (auto *b : h->batch_pool) destroy_batch(b);
+  for (auto *r : h->live_results) release_result(r);  // orphaned: the caller's free() just deletes
+  for (auto *b : h->live_batches) release_batch(b);
   cudaStreamDestroy(h->stream);
   delete h;
   return SGTD_OK;
@@ -237,17 +260,14 @@ int sgtd_build_descriptors(sgtd_handle *h, const sgtd_node *nodes, const int64_t
   }
   const int64_t total = off[nscans] - off[0];
   const sgtd_node *d_nodes = nodes;
-  DevBuf<sgtd_node> staged;
   if (total > 0 && !is_device_ptr(nodes)) {
-    SGTD_CUDA(h, staged.reserve((size_t)total, h->stream, false));
-    SGTD_CUDA(h, cudaMemcpyAsync(staged.p, nodes + off[0], (size_t)total * sizeof(sgtd_node), cudaMemcpyHostToDevice, h->stream));
-    d_nodes = staged.p - off[0];
+    SGTD_CUDA(h, h->stage_in.reserve((size_t)total * sizeof(sgtd_node), h->stream, false));
+    SGTD_CUDA(h, cudaMemcpyAsync(h->stage_in.p, nodes + off[0], (size_t)total * sizeof(sgtd_node), cudaMemcpyHostToDevice, h->stream));
+    d_nodes = reinterpret_cast<const sgtd_node *>(h->stage_in.p) - off[0];
   }
-  sgtd_desc_batch *b = new sgtd_desc_batch();
-  b->h = h;
+  sgtd_desc_batch *b = take_batch(h);
   int rc = build_descriptors(h, d_nodes, off, fid, b);
   cudaStreamSynchronize(h->stream);
-  staged.release();
   if (rc) { sgtd_desc_batch_free(b); return rc; }
   *out = b;
   return SGTD_OK;
@@ -258,8 +278,8 @@ int sgtd_desc_batch_upload(sgtd_handle *h, const sgtd_desc *descs, const int64_t
   if (!h || !out || nscans < 0 || (nscans > 0 && !scan_offsets)) SGTD_FAIL(h, SGTD_E_INVALID, "bad argument");
   SetDevice sd(h->device);
   cudaStream_t st = h->stream;
-  sgtd_desc_batch *b = new sgtd_desc_batch();
-  b->h = h; b->nscans = nscans;
+  sgtd_desc_batch *b = take_batch(h);
+  b->nscans = nscans;
   b->off.assign(nscans + 1, 0);
   if (nscans > 0) memcpy(b->off.data(), scan_offsets, (nscans + 1) * 8);
   b->n = b->off[nscans];
@@ -312,8 +332,10 @@ int sgtd_desc_batch_download(sgtd_handle *h, const sgtd_desc_batch *b, sgtd_desc
 
 int sgtd_desc_batch_free(sgtd_desc_batch *b) {
   if (!b) return SGTD_OK;
-  if (b->h) { SetDevice sd(b->h->device); b->rec.release(); b->vert.release(); b->d_off.release(); }
-  delete b;
+  sgtd_handle *h = b->h;
+  if (h) h->live_batches.erase(b);
+  if (h && h->batch_pool.size() < kPoolMax) { h->batch_pool.push_back(b); return SGTD_OK; }  // recycle
+  if (h) { SetDevice sd(h->device); destroy_batch(b); } else delete b;
   return SGTD_OK;
 }
 
@@ -390,9 +412,13 @@ int sgtd_search(sgtd_handle *h, const sgtd_desc_batch *queries, sgtd_search_resu
   if (!h || !queries || !out) SGTD_FAIL(h, SGTD_E_INVALID, "bad argument");
   SetDevice sd(h->device);
   *out = nullptr;
-  sgtd_search_result *r = new sgtd_search_result();
+  sgtd_search_result *r;
+  if (!h->result_pool.empty()) { r = h->result_pool.back(); h->result_pool.pop_back(); }
+  else r = new sgtd_search_result();
+  r->h = h;
+  h->live_results.insert(r);
   int rc = search(h, queries, r);
-  if (rc) { r->h = h; sgtd_result_free(r); return rc; }
+  if (rc) { sgtd_result_free(r); return rc; }
   *out = r;
   return SGTD_OK;
 }
@@ -463,12 +489,10 @@ int sgtd_result_stats(sgtd_handle *h, const sgtd_search_result *r, sgtd_vote_sta
 
 int sgtd_result_free(sgtd_search_result *r) {
   if (!r) return SGTD_OK;
-  if (r->h) {
-    SetDevice sd(r->h->device);
-    r->cands.release(); r->loops.release(); r->votes.release(); r->m_q.release(); r->m_g.release();
-    r->m_cell.release(); r->inl.release(); r->counters.release();
-  }
-  delete r;
+  sgtd_handle *h = r->h;
+  if (h) h->live_results.erase(r);
+  if (h && h->result_pool.size() < kPoolMax) { h->result_pool.push_back(r); return SGTD_OK; }  // recycle
+  if (h) { SetDevice sd(h->device); destroy_result(r); } else delete r;
   return SGTD_OK;
 }
 

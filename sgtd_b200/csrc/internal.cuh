@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/sgtd_b200.h"
@@ -123,6 +124,8 @@ struct sgtd_search_result {
   sgtd::DevBuf<int32_t> inl;            // inlier lists (same offsets as matches)
   sgtd::DevBuf<unsigned long long> counters;  // Q,P,Pfound,E,M
   sgtd_timings tm{};
+  cudaEvent_t ev[8] = {};  // created once, reused while the object sits in the handle's pool
+  bool have_ev = false;
 };
 
 struct sgtd_handle {
@@ -153,8 +156,14 @@ struct sgtd_handle {
   // per-keyframe key-sorted view (for match-list materialisation)
   sgtd::DevBuf<uint64_t> f_key;
   sgtd::DevBuf<uint32_t> f_g;
-  // scratch
+  // scratch + recycled objects: steady-state build/search calls do no cudaMalloc/cudaFree
   sgtd::DevBuf<unsigned char> scratch;
+  sgtd::DevBuf<unsigned char> stage_in;
+  std::vector<sgtd_search_result *> result_pool;
+  std::vector<sgtd_desc_batch *> batch_pool;
+  // objects handed to the caller and not yet freed; sgtd_destroy orphans them (h = nullptr)
+  std::unordered_set<sgtd_search_result *> live_results;
+  std::unordered_set<sgtd_desc_batch *> live_batches;
   int64_t frame_lo() const { return frames_per_rank ? (int64_t)rank * frames_per_rank : 0; }
   int64_t frames_local() const { return (int64_t)frame_off.size() - 1; }
 };

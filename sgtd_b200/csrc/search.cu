@@ -706,8 +706,11 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   const int64_t Fa = std::max<int64_t>(F, 1);
   r->h = h; r->nq = nq; r->k = k; r->F_local = F;
   const int64_t launches0 = h->launches;
-  cudaEvent_t ev[7];
-  for (auto &e : ev) SGTD_CUDA(h, cudaEventCreate(&e));
+  if (!r->have_ev) {
+    for (auto &e : r->ev) SGTD_CUDA(h, cudaEventCreate(&e));
+    r->have_ev = true;
+  }
+  cudaEvent_t *ev = r->ev;
   SGTD_CUDA(h, r->votes.reserve((size_t)nq * Fa, st, false)); r->votes.n = (size_t)nq * Fa;
   SGTD_CUDA(h, r->cands.reserve((size_t)nq * k, st, false)); r->cands.n = (size_t)nq * k;
   SGTD_CUDA(h, r->loops.reserve((size_t)std::max(nq, 1), st, false)); r->loops.n = nq;
@@ -737,6 +740,7 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   SGTD_CUDA(h, cudaEventRecord(ev[0], st));
   SGTD_CUDA(h, cudaMemsetAsync(r->votes.p, 0, (size_t)nq * Fa * 4, st));
   SGTD_CUDA(h, cudaMemsetAsync(r->counters.p, 0, 8 * 8, st));
+  SGTD_CUDA(h, cudaEventRecord(ev[7], st));
   if (nq > 0 && qb->n > 0 && h->rec.n > 0) {
     VoteParams V{};
     V.q = qb->rec.p; V.q_off = qb->d_off.p; V.nq = nq; V.nd = qb->n;
@@ -825,7 +829,8 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   }
   SGTD_CUDA(h, cudaEventRecord(ev[6], st));
   SGTD_CUDA(h, cudaStreamSynchronize(st));
-  r->tm.vote_ms = ev_ms(ev[0], ev[1]);
+  r->tm.clear_ms = ev_ms(ev[0], ev[7]);
+  r->tm.vote_ms = ev_ms(ev[7], ev[1]);
   r->tm.topk_ms = ev_ms(ev[1], ev[2]);
   r->tm.exchange_ms = ev_ms(ev[2], ev[3]);
   r->tm.collect_ms = ev_ms(ev[3], ev[4]);
@@ -833,7 +838,6 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   r->tm.total_ms = ev_ms(ev[0], ev[6]);
   r->tm.vote_launches = vote_launches;
   r->tm.total_launches = (int)(h->launches - launches0);
-  for (auto &e : ev) cudaEventDestroy(e);
   return SGTD_OK;
 }
 
