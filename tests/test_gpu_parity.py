@@ -163,3 +163,125 @@ def test_edge_cases(oracle_lib):
     ten = capi.make_nodes(grid[:10], labs[:10])
     gd, _ = mgr.build(ten).download()
     check_descs(gd, o.build(grid[:10], labs[:10]))
+
+
+def test_gpu_matches_committed_golden():
+    """GPU path against tests/golden/stage234_small.npz (no oracle at run time)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stage234_small.npz"))
+    cfg = synth.make_config(int(g["config_index"]), int(g["n_keyframes"]), int(g["n_queries"]))
+    xyz, lab, off = cfg["db"]
+    qx, ql, qo = cfg["queries"]
+    nf = off.shape[0] - 1
+    mgr = capi.STDescManager(device=0)
+    b = mgr.build(capi.make_nodes(xyz, lab), off, frame_ids=np.arange(nf, dtype=np.uint32))
+    _, goff = b.download(want_descs=False)
+    assert (np.diff(goff) == g["db_desc_counts"]).all()
+    mgr.add(b)
+    qb = mgr.build(capi.make_nodes(qx, ql), qo)
+    qd, qoff = qb.download()
+    res = mgr.search(qb)
+    loops, cands = res.download()
+    for q in range(qo.shape[0] - 1):
+        assert qd[qoff[q]:qoff[q + 1]].tobytes() == g[f"q{q}_descs"].tobytes()
+        assert (res.votes(q, nf) == g[f"q{q}_votes"]).all()
+        n = g[f"q{q}_cand_frame"].shape[0]
+        for k in ("frame", "votes", "nmatch", "score", "best_hyp", "ninlier"):
+            assert (cands[k][q, :n] == g[f"q{q}_cand_{k}"]).all(), k
+        ok = g[f"q{q}_cand_score"] >= 0
+        assert np.abs(cands["t"][q, :n][ok] - g[f"q{q}_cand_t"][ok]).max() <= POSE_T_TOL
+        for c in np.nonzero(ok)[0]:
+            assert rot_angle_deg(cands["R"][q, c], g[f"q{q}_cand_R"][c]) <= POSE_R_TOL_DEG
+        mg = np.concatenate([res.matches(q, c, int(cands["nmatch"][q, c]))[2] for c in range(n)])
+        assert (mg == g[f"q{q}_m_g"]).all()
+        assert loops["frame"][q] == int(g[f"q{q}_best"][0])
+
+
+def test_virtual_shards_equal_unsharded():
+    """Keyframe-range shards (3 handles on one GPU, no communicator): merging the per-shard
+    top-k lists reproduces the unsharded candidate list bit for bit, and the owning shard's
+    verification result equals the unsharded one."""
+    cfg = synth.make_config(2, 2000, 16)
+    xyz, lab, off = cfg["db"]
+    qx, ql, qo = cfg["queries"]
+    nf, nq, R = off.shape[0] - 1, qo.shape[0] - 1, 3
+    nodes, qnodes = capi.make_nodes(xyz, lab), capi.make_nodes(qx, ql)
+    full = capi.STDescManager(device=0)
+    b = full.build(nodes, off, frame_ids=np.arange(nf, dtype=np.uint32))
+    full.add(b)
+    _, fc = full.search(full.build(qnodes, qo)).download()
+    fpr = (nf + R - 1) // R
+    k = full.cfg.candidate_num
+    lv, lf, shard_c = [], [], []
+    for r in range(R):
+        m = capi.STDescManager(device=0)
+        m.shard_init(r, R, fpr, None)
+        m.add(m.build(nodes, off, frame_ids=np.arange(nf, dtype=np.uint32)))
+        assert m.current_frame_id_ == nf
+        lo, hi = r * fpr, min(nf, (r + 1) * fpr)
+        assert m.db_size == int((np.diff(b.download(want_descs=False)[1])[lo:hi]).sum())
+        _, c = m.search(m.build(qnodes, qo)).download()
+        assert ((c["frame"] == -1) | ((c["frame"] >= lo) & (c["frame"] < hi))).all()
+        lv.append(c["votes"]); lf.append(c["frame"]); shard_c.append(c)
+    for q in range(nq):
+        mv, mf = capi.merge_topk_host(np.stack([v[q] for v in lv]), np.stack([f[q] for f in lf]), k)
+        assert (mf == fc["frame"][q]).all() and (mv == fc["votes"][q]).all()
+        for c in range(k):
+            f = fc["frame"][q, c]
+            if f < 0:
+                break
+            own = shard_c[f // fpr][q]
+            j = int(np.nonzero(own["frame"] == f)[0][0])
+            for key in ("votes", "nmatch", "score", "ninlier", "best_hyp"):
+                assert own[key][j] == fc[key][q, c], key
+            assert (own["R"][j] == fc["R"][q, c]).all() and (own["t"][j] == fc["t"][q, c]).all()
+
+
+def test_full_size_properties():
+    """BASELINE config-3 sized DB (10k keyframes, 256 queries): size-independent properties."""
+    cfg = synth.make_config(2, 10000, 256)
+    xyz, lab, off = cfg["db"]
+    qx, ql, qo = cfg["queries"]
+    nf, nq = off.shape[0] - 1, qo.shape[0] - 1
+    mgr = capi.STDescManager(device=0)
+    mgr.add(mgr.build(capi.make_nodes(xyz, lab), off, frame_ids=np.arange(nf, dtype=np.uint32)))
+    qb = mgr.build(capi.make_nodes(qx, ql), qo)
+    res = mgr.search(qb)
+    loops, cands = res.download()
+    stats, _ = res.stats()
+    # checksum of checksums: votes over all queries and keyframes == matches counted by the kernel
+    tot = sum(int(res.votes(q, nf).sum()) for q in range(0, nq, 16))
+    sub, _ = None, None
+    assert stats["M"] >= tot > 0 and stats["Q"] == len(qb)
+    k = mgr.cfg.candidate_num
+    for q in range(0, nq, 16):
+        v = res.votes(q, nf)
+        order = np.lexsort((np.arange(nf), -v))[:k]
+        order = order[v[order] >= 5]
+        n = loops["ncand"][q]
+        assert (cands["frame"][q, :n] == order).all() and (cands["votes"][q, :n] == v[order]).all()
+        # ranking is sorted by (votes desc, frame asc); nmatch == votes; inliers <= matches
+        assert (cands["nmatch"][q, :n] == cands["votes"][q, :n]).all()
+        assert (cands["ninlier"][q, :n] <= cands["nmatch"][q, :n]).all()
+        sc = cands["score"][q, :n]
+        assert ((sc == -1) | (sc >= 4)).all()
+        best = -1 if (sc <= 0).all() else cands["frame"][q, int(np.argmax(sc))]
+        assert loops["frame"][q] == best
+        # rotations are proper, match lists ordered and owned by the candidate keyframe
+        for c in range(min(n, 3)):
+            if sc[c] >= 0:
+                Rm = cands["R"][q, c].reshape(3, 3)
+                assert np.abs(Rm @ Rm.T - np.eye(3)).max() < 1e-9 and abs(np.linalg.det(Rm) - 1) < 1e-9
+            m_q, m_cell, m_g = res.matches(q, c, int(cands["nmatch"][q, c]))
+            key = m_q.astype(np.int64) * (1 << 40) + m_cell.astype(np.int64) * (1 << 33) + m_g
+            assert (np.diff(key) > 0).all()
+            assert (mgr.db_fetch(m_g[:64])["frame"] == cands["frame"][q, c]).all()
+    # idempotence: the same batch again gives identical results
+    loops2, cands2 = mgr.search(qb).download()
+    assert loops2.tobytes() == loops.tobytes()
+    for key in ("frame", "votes", "score", "R", "t"):
+        assert (cands2[key] == cands[key]).all()
+    # the place is found: best keyframe within 10 m of the query pose for almost all queries
+    P = cfg["world"]["poses"]
+    hit = [np.hypot(*(P[loops["frame"][q], :2] - cfg["qposes"][q, :2])) < 10 for q in range(nq) if loops["frame"][q] >= 0]
+    assert len(hit) >= 0.95 * nq and np.mean(hit) >= 0.95
