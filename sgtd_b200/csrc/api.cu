@@ -1,6 +1,4 @@
 // api.cu -- the extern "C" surface of libsgtd_b200.so (see include/sgtd_b200.h).
-#include <nccl.h>
-
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +7,7 @@
 #include <sstream>
 
 #include "internal.cuh"
+#include "nccl_dyn.h"
 
 using namespace sgtd;
 
@@ -220,7 +219,7 @@ int sgtd_destroy(sgtd_handle *h) {
   if (!h) return SGTD_OK;
   SetDevice sd(h->device);
   cudaStreamSynchronize(h->stream);
-  if (h->nccl) ncclCommDestroy((ncclComm_t)h->nccl);
+  if (h->nccl) nccl_api().CommDestroy((ncclComm_t)h->nccl);
   h->rec.release(); h->vert.release(); h->d_frame_off.release();
   h->v_s0.release(); h->v_s1.release(); h->v_s2.release(); h->v_frame.release();
   h->table.release(); h->f_key.release(); h->f_g.release(); h->scratch.release(); h->stage_in.release();
@@ -527,7 +526,7 @@ int sgtd_nccl_unique_id(void *id128) {
   if (!id128) return SGTD_E_INVALID;
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId");
   ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) return SGTD_E_NCCL;
+  if (!nccl_api().ok || nccl_api().GetUniqueId(&id) != ncclSuccess) return SGTD_E_NCCL;
   memcpy(id128, &id, 128);
   return SGTD_OK;
 }
@@ -542,7 +541,8 @@ int sgtd_shard_init(sgtd_handle *h, int32_t rank, int32_t nranks, int64_t frames
     ncclUniqueId id;
     memcpy(&id, nccl_unique_id, 128);
     ncclComm_t comm;
-    if (ncclCommInitRank(&comm, nranks, id, rank) != ncclSuccess) SGTD_FAIL(h, SGTD_E_NCCL, "ncclCommInitRank");
+    if (!nccl_api().ok) SGTD_FAIL(h, SGTD_E_NCCL, "libnccl.so.2 not found");
+    if (nccl_api().CommInitRank(&comm, nranks, id, rank) != ncclSuccess) SGTD_FAIL(h, SGTD_E_NCCL, "ncclCommInitRank");
     h->nccl = comm;
   }
   return SGTD_OK;

@@ -1,0 +1,33 @@
+// nccl_dyn.h -- NCCL is bound at run time (dlopen), not at link time.
+// libsgtd_b200.so must load on hosts without NCCL (single-GPU use) and must share
+// whatever libnccl.so.2 the process already has (e.g. the newer one PyTorch bundles)
+// instead of pinning the system copy through DT_NEEDED.  Only the four entry points
+// the sharded search needs are resolved.
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace sgtd {
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  bool ok = false;
+};
+inline const NcclApi &nccl_api() {
+  static NcclApi api = [] {
+    NcclApi a;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return a;
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(lib, "ncclAllGather"));
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather;
+    return a;
+  }();
+  return api;
+}
+}  // namespace sgtd

@@ -11,9 +11,8 @@
 // All FP64 comparisons are the reference's, reformulated without changing any
 // outcome: "sqrt(x) < t" is evaluated as "x < sq_threshold(t)".
 #include <cub/device/device_scan.cuh>
-#include <nccl.h>
-
 #include "internal.cuh"
+#include "nccl_dyn.h"
 
 namespace sgtd {
 
@@ -765,8 +764,8 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   const int32_t *tv = lv, *tf = lf;
   if (h->nranks > 1 && h->nccl && nq > 0) {
     ncclComm_t comm = (ncclComm_t)h->nccl;
-    if (ncclAllGather(lv, gv, nslot, ncclInt32, comm, st) != ncclSuccess) SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(votes)");
-    if (ncclAllGather(lf, gf, nslot, ncclInt32, comm, st) != ncclSuccess) SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(frames)");
+    if (nccl_api().AllGather(lv, gv, nslot, ncclInt32, comm, st) != ncclSuccess) SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(votes)");
+    if (nccl_api().AllGather(lf, gf, nslot, ncclInt32, comm, st) != ncclSuccess) SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(frames)");
     k_merge<<<nq, 128, (size_t)h->nranks * k * 8, st>>>(gv, gf, h->nranks, nq, k, mv, mf);
     SGTD_LAUNCHED(h);
     SGTD_CUDA(h, cudaGetLastError());
@@ -814,7 +813,7 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   if (h->nranks > 1 && h->nccl && nq > 0) {
     ncclComm_t comm = (ncclComm_t)h->nccl;
     sgtd_candidate *gc = (sgtd_candidate *)(S + o_gc);
-    if (ncclAllGather(r->cands.p, gc, nslot * sizeof(sgtd_candidate), ncclUint8, comm, st) != ncclSuccess)
+    if (nccl_api().AllGather(r->cands.p, gc, nslot * sizeof(sgtd_candidate), ncclUint8, comm, st) != ncclSuccess)
       SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(candidates)");
     // keep this rank's own offsets for owned slots: k_pick_owner copies the owner's record, which for
     // owned slots is this rank's own record.
