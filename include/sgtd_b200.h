@@ -244,6 +244,16 @@ int sgtd_extract_instances(sgtd_handle *h, const float *points,
                            int32_t *point_instance, sgtd_node *nodes,
                            int32_t cap_nodes, int32_t *n_nodes,
                            int32_t *n_instances);
+/* Batched form: scan s is points[scan_offsets[s] .. scan_offsets[s+1]).  nodes of scan s
+ * are written to nodes[node_offsets[s] .. node_offsets[s+1]); point_instance (total
+ * points, may be NULL) and n_instances (nscans, may be NULL) as above.  Pointers may be
+ * host or device memory; node_offsets / n_instances are host arrays. */
+int sgtd_extract_instances_batch(sgtd_handle *h, const float *points,
+                                 const uint32_t *labels,
+                                 const int64_t *scan_offsets, int32_t nscans,
+                                 int32_t *point_instance, sgtd_node *nodes,
+                                 int64_t cap_nodes, int64_t *node_offsets,
+                                 int32_t *n_instances);
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,12 @@ def lib():
                                  C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(OrcStats), C.c_int32]
         L.orc_triangle_solver.argtypes = [C.c_void_p] * 4
         L.orc_jacobi_svd3.argtypes = [C.c_void_p] * 4
+        L.orc_dcvc.restype = C.c_int32
+        L.orc_dcvc.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
+                               C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_extract_instances.restype = C.c_int32
+        L.orc_extract_instances.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -178,3 +184,37 @@ def jacobi_svd3(A):
     V = np.zeros(9)
     lib().orc_jacobi_svd3(_p(A), _p(U), _p(s), _p(V))
     return U.reshape(3, 3), s, V.reshape(3, 3)
+
+
+def dcvc(xyz, startR=0.35, deltaR=0.0004, deltaP=1.2, deltaA=1.2, minSeg=300):
+    """clusterManager::segmentPointCloud on one class cloud.
+    Returns (label_info[n], cluster_of[n], n_clusters, (width, height, polarNum))."""
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    n = xyz.shape[0]
+    lab = np.full(n, -1, np.int32)
+    cl = np.full(n, -1, np.int32)
+    grid = np.zeros(3, np.int32)
+    nc = lib().orc_dcvc(_p(xyz), n, startR, deltaR, deltaP, deltaA, minSeg, _p(lab), _p(cl), _p(grid))
+    return lab, cl, int(nc), tuple(int(x) for x in grid)
+
+
+def extract_instances(points, labels):
+    """gen_labels + gen_graphs nodes.  points [n,4] float32, labels [n] uint32.
+    Returns dict(point_instance[n], node_xyz[k,3], node_label[k], node_inst[k], n_instances)."""
+    points = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
+    labels = np.ascontiguousarray(labels, np.uint32)
+    n = points.shape[0]
+    cap = 1 << 16
+    pi = np.full(n, -1, np.int32)
+    nx = np.zeros((cap, 3), np.float32)
+    nl = np.zeros(cap, np.uint32)
+    ni = np.zeros(cap, np.int32)
+    nn = C.c_int32(0)
+    ninst = C.c_int32(0)
+    rc = lib().orc_extract_instances(_p(points), _p(labels), n, _p(pi), _p(nx), _p(nl), _p(ni), cap,
+                                     C.byref(nn), C.byref(ninst))
+    if rc:
+        raise RuntimeError("orc_extract_instances: capacity")
+    k = nn.value
+    return dict(point_instance=pi, node_xyz=nx[:k].copy(), node_label=nl[:k].copy(), node_inst=ni[:k].copy(),
+                n_instances=ninst.value)

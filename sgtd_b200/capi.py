@@ -88,6 +88,7 @@ SYMBOLS = {
     "sgtd_nccl_unique_id": (C.c_int, [_VP]),
     "sgtd_shard_init": (C.c_int, [_VP, _I32, _I32, _I64, _VP]),
     "sgtd_extract_instances": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _VP, _I32, _VP, _VP]),
+    "sgtd_extract_instances_batch": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _VP, _I64, _VP, _VP]),
 }
 
 _lib = None
@@ -335,6 +336,25 @@ class STDescManager:
 
     def synchronize(self):
         self._chk(lib().sgtd_synchronize(self._h))
+
+    # -- gen_labels + gen_graphs (stage 1), batched ----------------------------------------------
+    def extract_instances(self, points, labels, offsets=None, want_membership=True):
+        """points [N,4] float32 (KITTI .bin layout), labels [N] uint32 (.label layout).
+        Returns (nodes NODE_DTYPE[...], node_offsets[nscans+1], point_instance[N] or None, n_instances[nscans])."""
+        points = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
+        labels = np.ascontiguousarray(labels, np.uint32)
+        if offsets is None:
+            offsets = np.array([0, points.shape[0]], np.int64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        ns = offsets.shape[0] - 1
+        cap = 4096 * max(ns, 1)
+        nodes = np.zeros(cap, NODE_DTYPE)
+        noff = np.zeros(ns + 1, np.int64)
+        ninst = np.zeros(max(ns, 1), np.int32)
+        pi = np.full(points.shape[0], -1, np.int32) if want_membership else None
+        self._chk(lib().sgtd_extract_instances_batch(self._h, _p(points), _p(labels), _p(offsets), ns, _p(pi),
+                                                     _p(nodes), cap, _p(noff), _p(ninst)))
+        return nodes[:noff[ns]].copy(), noff, pi, ninst[:ns]
 
 
 def nccl_unique_id():

@@ -548,10 +548,4 @@ int sgtd_shard_init(sgtd_handle *h, int32_t rank, int32_t nranks, int64_t frames
   return SGTD_OK;
 }
 
-// ---- stage 1 (instances.cu) ----------------------------------------------------------------
-__attribute__((weak)) int sgtd_extract_instances(sgtd_handle *h, const float *, const uint32_t *, int64_t, int32_t *,
-                                                 sgtd_node *, int32_t, int32_t *, int32_t *) {
-  SGTD_FAIL(h, SGTD_E_INVALID, "sgtd_extract_instances: stage 1 not built into this library");
-}
-
 }  // extern "C"

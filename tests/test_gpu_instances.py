@@ -1,0 +1,125 @@
+"""GPU parity of stage 1 (instance extraction) against the literal CPU oracle:
+instance ids, per-point membership, node labels and node order bit-exact; centroids
+bit-equal (sequential float32 sums in the reference's order)."""
+import numpy as np
+import pytest
+
+from sgtd_b200 import capi, synth_scan
+
+pytestmark = pytest.mark.gpu
+
+
+def compare(mgr, orc, pts, lab):
+    nodes, noff, pi, ninst = mgr.extract_instances(pts, lab)
+    r = orc.extract_instances(pts, lab)
+    assert ninst[0] == r["n_instances"]
+    assert (pi == r["point_instance"]).all(), np.nonzero(pi != r["point_instance"])[0][:10]
+    assert nodes.shape[0] == r["node_label"].shape[0]
+    assert (nodes["label"] == r["node_label"]).all()
+    got = np.column_stack([nodes["x"], nodes["y"], nodes["z"]])
+    assert got.tobytes() == r["node_xyz"].tobytes()
+    return nodes, r
+
+
+@pytest.fixture(scope="module")
+def mgr():
+    return capi.STDescManager(device=0)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_synthetic_scans_match_oracle(mgr, oracle_lib, seed):
+    pts, lab = synth_scan.make_scan(1000 + seed)
+    nodes, r = compare(mgr, oracle_lib, pts, lab)
+    assert nodes.shape[0] >= 10
+
+
+def test_random_clouds_stress_order_dependence(mgr, oracle_lib):
+    """Dense random blobs: many merges, head-only voxels, invisible top-pitch voxels."""
+    rng = np.random.default_rng(7)
+    for it in range(12):
+        n = int(rng.integers(300, 6000))
+        k = int(rng.integers(2, 12))
+        centers = rng.uniform(-40, 40, (k, 3)) * np.array([1, 1, 0.1])
+        which = rng.integers(0, k, n)
+        xyz = centers[which] + rng.normal(0, rng.uniform(0.2, 3.0), (n, 3)) * np.array([1, 1, 0.5])
+        pts = np.column_stack([xyz, rng.uniform(0, 1, n)]).astype(np.float32)
+        lab = rng.choice([12, 13, 15, 16, 17, 18, 11, 4, 5], n).astype(np.uint32)
+        compare(mgr, oracle_lib, pts, lab)
+
+
+def test_dcvc_labels_per_class(mgr, oracle_lib):
+    """Membership of every DCVC cluster (not only those above minSeg) through point_instance of a
+    single-class cloud with minSeg 5 (class 17)."""
+    rng = np.random.default_rng(11)
+    n = 4000
+    xyz = rng.uniform(-30, 30, (n, 3)) * np.array([1, 1, 0.05])
+    pts = np.column_stack([xyz, np.zeros(n)]).astype(np.float32)
+    lab = np.full(n, 17, np.uint32)
+    nodes, noff, pi, ninst = mgr.extract_instances(pts, lab)
+    _, cl, nc, _ = oracle_lib.dcvc(pts[:, :3], minSeg=5)
+    assert ninst[0] == nc and (pi == cl).all()
+
+
+def test_policies_and_edge_cases(mgr, oracle_lib):
+    rng = np.random.default_rng(13)
+    n = 5000
+    xyz = rng.uniform(-25, 25, (n, 3)) * np.array([1, 1, 0.1])
+    pts = np.column_stack([xyz, np.zeros(n)]).astype(np.float32)
+    sem = rng.choice([0, 8, 9, 10, 12, 4, 5, 13, 19, 14], n)
+    inst = np.zeros(n, np.int64)
+    m = sem == 4          # other-vehicle with GT instance ids -> one instance per id with > 20 points
+    inst[m] = rng.choice([0, 3, 7, 200, 65535], m.sum(), p=[0.3, 0.3, 0.3, 0.09, 0.01])
+    m = sem == 13         # fence: all points share one non-zero id -> GT branch with a single id
+    inst[m] = 9
+    lab = (sem | (inst << 16)).astype(np.uint32)
+    compare(mgr, oracle_lib, pts, lab)
+    # points outside (0.5, 120) m are hashed with a zero polar record
+    far = pts.copy()
+    far[:50, :3] *= 100.0
+    far[50:80, :3] *= 0.001
+    compare(mgr, oracle_lib, far, np.where(sem == 12, 12, 16).astype(np.uint32))
+    # a scan with no clustered class at all, and an empty scan
+    nodes, noff, pi, ninst = mgr.extract_instances(pts, np.full(n, 8, np.uint32))
+    assert nodes.shape[0] == 0 and ninst[0] == 0 and (pi == -1).all()
+    nodes, noff, pi, ninst = mgr.extract_instances(np.zeros((0, 4), np.float32), np.zeros(0, np.uint32))
+    assert nodes.shape[0] == 0
+    with pytest.raises(capi.SgtdError):
+        mgr.extract_instances(pts, np.full(n, 40, np.uint32))
+
+
+def test_batch_equals_single(mgr, oracle_lib):
+    scans = [synth_scan.make_scan(2000 + s) for s in range(5)]
+    off = np.concatenate([[0], np.cumsum([p.shape[0] for p, _ in scans])]).astype(np.int64)
+    P = np.concatenate([p for p, _ in scans])
+    L = np.concatenate([l for _, l in scans])
+    nodes, noff, pi, ninst = mgr.extract_instances(P, L, off)
+    for s, (p, l) in enumerate(scans):
+        r = oracle_lib.extract_instances(p, l)
+        sl = slice(noff[s], noff[s + 1])
+        assert (nodes["label"][sl] == r["node_label"]).all()
+        assert np.column_stack([nodes["x"][sl], nodes["y"][sl], nodes["z"][sl]]).tobytes() == r["node_xyz"].tobytes()
+        assert (pi[off[s]:off[s + 1]] == r["point_instance"]).all()
+        assert ninst[s] == r["n_instances"]
+
+
+def test_scan_to_pose_pipeline(mgr, oracle_lib):
+    """Stages 1-4 chained on the GPU == chained oracle: a scan re-observed with new noise is
+    localised against a tiny map built from scans."""
+    m = capi.STDescManager(device=0)
+    o = oracle_lib.Oracle()
+    for s in range(6):
+        pts, lab = synth_scan.make_scan(3000 + 10 * s)
+        nodes, *_ = m.extract_instances(pts, lab, want_membership=False)
+        r = oracle_lib.extract_instances(pts, lab)
+        assert (nodes["label"] == r["node_label"]).all()
+        m.add(m.build(nodes))
+        o.add(o.build(r["node_xyz"], r["node_label"]))
+    scene = synth_scan.make_scene(3020)
+    pts, lab = synth_scan.render(scene, 999)          # same place as map keyframe 2, new noise
+    nodes, *_ = m.extract_instances(pts, lab, want_membership=False)
+    r = oracle_lib.extract_instances(pts, lab)
+    loops, cands = m.search(m.build(nodes)).download()
+    ro = o.search(o.build(r["node_xyz"], r["node_label"]))
+    assert loops["frame"][0] == ro["best"][0] == 2
+    n = ro["n"]
+    assert (cands["frame"][0, :n] == ro["cands"]["frame"]).all() and (cands["score"][0, :n] == ro["cands"]["score"]).all()
