@@ -87,6 +87,16 @@ def test_policies_and_edge_cases(mgr, oracle_lib):
         mgr.extract_instances(pts, np.full(n, 40, np.uint32))
 
 
+def test_gpu_matches_stage1_golden(mgr):
+    """GPU stage 1 against the committed fixture (no oracle at run time)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stage1_small.npz"))
+    nodes, noff, pi, ninst = mgr.extract_instances(g["points"], g["labels"])
+    assert ninst[0] == int(g["n_instances"]) and (pi == g["point_instance"]).all()
+    assert (nodes["label"] == g["node_label"]).all()
+    assert np.column_stack([nodes["x"], nodes["y"], nodes["z"]]).tobytes() == g["node_xyz"].tobytes()
+
+
 def test_batch_equals_single(mgr, oracle_lib):
     scans = [synth_scan.make_scan(2000 + s) for s in range(5)]
     off = np.concatenate([[0], np.cumsum([p.shape[0] for p, _ in scans])]).astype(np.int64)
