@@ -111,6 +111,25 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the vote kernel from the ncu --set full
+# capture of THIS workload (profiles/r01b_ncu_summary.md); None for any other workload / sharding.
+NCU_TRAFFIC = {("k_vote_join", 100000, 1024, 1): 63.378449e9 + 15.422655e9,
+               ("k_vote", 100000, 1024, 1): 355.053564e9 + 20.017364e9}
+ROOFLINE_NOTE = ("achieved = SURVEY 8d per-probe byte model (32Q+16P+28E+12M, counters from the kernel) / CUDA-event "
+                 "time of the vote kernel. k_vote_join streams each bucket once per run of sorted probes instead of "
+                 "once per probe, so its real DRAM traffic (`traffic`, ncu) is ~4.9x below the model and `frac` "
+                 "exceeds 1; `traffic_frac_of_peak` is the HBM utilisation of the bytes actually moved. "
+                 "SGTD_VOTE_MODE=stream selects the per-probe kernel the model describes (0.95 of peak, 3.1x slower).")
+
+
+def result_crc(loops, cands):
+    import zlib
+    c = 0
+    for a in (loops["frame"], loops["score"], cands["frame"], cands["votes"], cands["score"]):
+        c = zlib.crc32(np.ascontiguousarray(a).tobytes(), c)
+    return c
+
+
 def algorithmic_bytes(st):
     return 32 * st["Q"] + 16 * st["P"] + 28 * st["E"] + 12 * st["M"]
 
@@ -294,6 +313,8 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         vms = float(np.mean(vote_ms))
+        vote_kernel = "k_vote" if os.environ.get("SGTD_VOTE_MODE") == "stream" else "k_vote_join"
+        traffic = NCU_TRAFFIC.get((vote_kernel, nkf, nq, world))
         ach = algorithmic_bytes(stats) / (vms * 1e-3) / 1e9      # this rank's kernel, this rank's bytes
         found = int((loops["frame"] >= 0).sum())
         gt = cfg["gt"]
@@ -315,12 +336,17 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(qnodes.nbytes + qo.nbytes),
                     "d2h_bytes_per_step": int(loops_pin.numel() + cands_pin.numel())},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_vote", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": vote_kernel, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algorithmic_bytes(stats), "avg_launch_ms": vms,
-                         "counters": stats},
+                         "counters": stats,
+                         "traffic_gbs": (traffic / (vms * 1e-3) / 1e9) if traffic else None,
+                         "traffic_frac_of_peak": (traffic / (vms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "note": ROOFLINE_NOTE},
             "stage_ms": {kk: round(vv, 3) for kk, vv in stage.items()},
             "recall": {"found": found, "within_10m": ok, "queries": nq},
+            # checksum of (best frame, score, candidate frames/votes/scores): identical for every N
+            "result_crc": result_crc(loops, np.frombuffer(cands_pin.numpy().tobytes(), capi.CAND_DTYPE)),
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:

@@ -137,7 +137,8 @@ typedef struct sgtd_vote_stats {
  * the handle's stream). */
 typedef struct sgtd_timings {
   float clear_ms;  /* zeroing the vote rows */
-  float vote_ms;   /* the vote kernel alone */
+  float vote_ms;   /* the vote kernel alone (k_vote_join, or k_vote in stream mode) */
+  float probe_ms;  /* join mode: probe emission + radix sort of (bucket, descriptor) pairs */
   float topk_ms, exchange_ms, collect_ms, verify_ms, total_ms;
   int32_t vote_launches, total_launches;
 } sgtd_timings;

@@ -46,7 +46,7 @@ class VoteStats(C.Structure):
 
 
 class Timings(C.Structure):
-    _fields_ = [(k, C.c_float) for k in ("clear_ms", "vote_ms", "topk_ms", "exchange_ms", "collect_ms", "verify_ms", "total_ms")] + \
+    _fields_ = [(k, C.c_float) for k in ("clear_ms", "vote_ms", "probe_ms", "topk_ms", "exchange_ms", "collect_ms", "verify_ms", "total_ms")] + \
                [("vote_launches", C.c_int32), ("total_launches", C.c_int32)]
 
 

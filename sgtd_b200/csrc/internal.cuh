@@ -124,7 +124,7 @@ struct sgtd_search_result {
   sgtd::DevBuf<int32_t> inl;            // inlier lists (same offsets as matches)
   sgtd::DevBuf<unsigned long long> counters;  // Q,P,Pfound,E,M
   sgtd_timings tm{};
-  cudaEvent_t ev[8] = {};  // created once, reused while the object sits in the handle's pool
+  cudaEvent_t ev[10] = {};  // created once, reused while the object sits in the handle's pool
   bool have_ev = false;
 };
 

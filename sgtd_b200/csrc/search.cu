@@ -10,15 +10,22 @@
 //
 // All FP64 comparisons are the reference's, reformulated without changing any
 // outcome: "sqrt(x) < t" is evaluated as "x < sq_threshold(t)".
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cstdlib>
+#include <cstring>
+
 #include "internal.cuh"
 #include "nccl_dyn.h"
 
 namespace sgtd {
 
 // ============================ vote kernel =======================================
+struct QAux;
 struct VoteParams {
   const DescRec *q;        // query descriptors of the whole batch
+  const QAux *aux;         // per-descriptor threshold / probe mask / query index
+  const uint32_t *perm;    // processing order (descriptors sorted by cell key for L2 locality) or null
   const int64_t *q_off;    // nq+1
   int nq;
   int64_t nd;              // total query descriptors
@@ -53,6 +60,44 @@ __device__ __forceinline__ bool probe_key(const DescRec &r, int ord, uint64_t &k
   return in_ball && px >= 0 && py >= 0 && pz >= 0;
 }
 
+// key of probe `ord` only (ball test already known)
+__device__ __forceinline__ uint64_t probe_cell_key(const DescRec &r, int ord) {
+  const int ix = ord / 9 - 1, iy = (ord / 3) % 3 - 1, iz = ord % 3 - 1;
+  const int px = __double2int_rz(__dadd_rn(r.s[0], (double)ix));
+  const int py = __double2int_rz(__dadd_rn(r.s[1], (double)iy));
+  const int pz = __double2int_rz(__dadd_rn(r.s[2], (double)iz));
+  return pack_key((uint32_t)px, (uint32_t)py, (uint32_t)pz, r.code);
+}
+
+// Per query descriptor, computed once per batch and shared by k_vote and k_collect:
+// the squared rough-distance threshold, the 27-bit mask of probes that pass the
+// 1.5-ball test, and the query (scan) index of the descriptor.
+struct __align__(16) QAux {
+  double thr2;
+  uint32_t mask;
+  uint32_t qi;
+};
+__global__ void k_qaux(const DescRec *q, const int64_t *q_off, int nq, int64_t nd, double rough, QAux *aux,
+                       uint64_t *skey, uint32_t *sidx) {
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nd) return;
+  const DescRec r = q[d];
+  QAux a;
+  a.thr2 = sq_threshold(__dmul_rn(norm3(r.s[0], r.s[1], r.s[2]), rough));
+  uint32_t m = 0;
+  for (int ord = 0; ord < 27; ++ord) { uint64_t key; if (probe_key(r, ord, key)) m |= 1u << ord; }
+  a.mask = m;
+  int lo = 0, hi = nq - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (q_off[mid] <= d) lo = mid; else hi = mid - 1; }
+  a.qi = (uint32_t)lo;
+  aux[d] = a;
+  if (skey) {  // label code major, then the descriptor's own cell: neighbours in this order share buckets
+    const uint64_t k = probe_cell_key(r, 13);
+    skey[d] = ((k & 0xFFFull) << 48) | (k >> 12);
+    sidx[d] = (uint32_t)d;
+  }
+}
+
 __device__ __forceinline__ bool table_find(const Bucket *table, uint64_t mask, uint64_t key, uint32_t &off,
                                            uint32_t &cnt) {
   uint64_t pos = mix64(key) & mask;
@@ -66,34 +111,27 @@ __device__ __forceinline__ bool table_find(const Bucket *table, uint64_t mask, u
 }
 
 constexpr int kVoteThreads = 256;
+constexpr int kVoteUnroll = 4;
 
 // One warp per query descriptor (persistent, strided).  Lanes 0..26 evaluate the
 // 27 probes and look their bucket up; the warp then streams every found bucket
 // with coalesced SoA loads (8 B x 3 + 4 B per entry) and votes with fire-and-
 // forget reductions (RED.ADD) into the query's per-keyframe counter row.
+template <bool kDoVote>
 __global__ void __launch_bounds__(kVoteThreads) k_vote(VoteParams P) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * kVoteThreads + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * kVoteThreads) >> 5;
   unsigned long long cP = 0, cPf = 0, cE = 0, cM = 0, cQ = 0;
-  int qi = 0;
-  for (int64_t d = warp; d < P.nd; d += nwarps) {
-    // query index of descriptor d (uniform binary search over q_off)
-    if (!(d >= P.q_off[qi] && d < P.q_off[qi + 1])) {
-      int lo = 0, hi = P.nq - 1;
-      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (P.q_off[mid] <= d) lo = mid; else hi = mid - 1; }
-      qi = lo;
-    }
+  for (int64_t w = warp; w < P.nd; w += nwarps) {
+    const int64_t d = P.perm ? (int64_t)P.perm[w] : w;
     const DescRec r = P.q[d];
-    const double thr = __dmul_rn(norm3(r.s[0], r.s[1], r.s[2]), P.rough);
-    const double thr2 = sq_threshold(thr);
+    const QAux a = P.aux[d];
+    const double thr2 = a.thr2;
+    const int qi = (int)a.qi;
     uint32_t off = 0, cnt = 0;
-    bool pass = false;
-    if (lane < 27) {
-      uint64_t key;
-      pass = probe_key(r, lane, key);
-      if (pass && !table_find(P.table, P.mask, key, off, cnt)) cnt = 0;
-    }
+    const bool pass = (a.mask >> lane) & 1u;
+    if (pass && !table_find(P.table, P.mask, probe_cell_key(r, lane), off, cnt)) cnt = 0;
     const unsigned m_pass = __ballot_sync(0xffffffffu, pass);
     unsigned m_found = __ballot_sync(0xffffffffu, cnt > 0);
     cQ += 1; cP += __popc(m_pass); cPf += __popc(m_found);
@@ -104,20 +142,27 @@ __global__ void __launch_bounds__(kVoteThreads) k_vote(VoteParams P) {
       const uint32_t o = __shfl_sync(0xffffffffu, off, src);
       const uint32_t n = __shfl_sync(0xffffffffu, cnt, src);
       cE += n;
-      for (uint32_t e0 = 0; e0 < n; e0 += 32) {
-        const uint32_t e = e0 + lane;
-        bool hit = false;
-        uint32_t f = 0;
-        if (e < n) {
-          const size_t idx = (size_t)o + e;
-          const double a = __ldg(P.s0 + idx), b = __ldg(P.s1 + idx), c = __ldg(P.s2 + idx);
-          f = __ldg(P.fr + idx);
-          const double d2 = sqn3(__dsub_rn(r.s[0], a), __dsub_rn(r.s[1], b), __dsub_rn(r.s[2], c));
-          // (src.frame_id_ - db.frame_id_) > 0 on unsigned == "!=" (STDesc.cpp:373)
-          hit = (f + P.frame_lo != r.frame) && (d2 < thr2);
+      // kVoteUnroll x 32 entries per trip: all loads are issued before the first use so
+      // that each warp keeps 4*kVoteUnroll independent 128/256-byte requests in flight.
+      for (uint32_t e0 = 0; e0 < n; e0 += 32 * kVoteUnroll) {
+        double a[kVoteUnroll], b[kVoteUnroll], c[kVoteUnroll];
+        uint32_t f[kVoteUnroll];
+#pragma unroll
+        for (int u = 0; u < kVoteUnroll; ++u) {
+          const uint32_t e = e0 + 32 * u + lane;
+          const size_t idx = (size_t)o + (e < n ? e : n - 1);  // clamp: tail lanes re-read the last entry
+          a[u] = __ldg(P.s0 + idx); b[u] = __ldg(P.s1 + idx); c[u] = __ldg(P.s2 + idx);
+          f[u] = __ldg(P.fr + idx);
         }
-        if (hit) atomicAdd(row + f, 1u);
-        cM += __popc(__ballot_sync(0xffffffffu, hit));
+#pragma unroll
+        for (int u = 0; u < kVoteUnroll; ++u) {
+          const uint32_t e = e0 + 32 * u + lane;
+          const double d2 = sqn3(__dsub_rn(r.s[0], a[u]), __dsub_rn(r.s[1], b[u]), __dsub_rn(r.s[2], c[u]));
+          // (src.frame_id_ - db.frame_id_) > 0 on unsigned == "!=" (STDesc.cpp:373)
+          const bool hit = (e < n) && (f[u] + P.frame_lo != r.frame) && (d2 < thr2);
+          if (kDoVote && hit) atomicAdd(row + f[u], 1u);
+          cM += __popc(__ballot_sync(0xffffffffu, hit));
+        }
       }
     }
   }
@@ -126,6 +171,142 @@ __global__ void __launch_bounds__(kVoteThreads) k_vote(VoteParams P) {
     atomicAdd(P.counters + 3, cE);
   }
   if (lane == 0 && P.counters) atomicAdd(P.counters + 4, cM);
+}
+
+// ============================ vote as a bucket-major join ===========================
+// The per-probe formulation above re-reads every bucket once per probe (a 1,024-query
+// batch probes the average bucket ~20 times).  The join inverts the loop nest:
+//   k_probe_emit   (descriptor, bucket slot) pairs of all probes that found a bucket
+//   cub radix sort pairs by bucket slot
+//   k_vote_join    one warp per segment of kJoinSeg consecutive sorted probes: for every
+//                  run of equal slots the bucket is streamed ONCE (entries in registers,
+//                  kVoteUnroll x 32 per trip) and tested against all probes of the run
+//                  (their side lengths / thresholds / vote rows sit in shared memory).
+// Same pair tests, same votes; HBM traffic drops by the run length.
+constexpr int kJoinSeg = 16;
+
+struct EmitParams2 {
+  const DescRec *q; const QAux *aux; int64_t nd;
+  const Bucket *table; uint64_t mask;
+  uint32_t *pkey, *pval;
+  unsigned long long *cursor, *counters;
+  uint32_t group_shift, group_div;  // sort key = (query / group_div) << group_shift | slot
+};
+
+__global__ void __launch_bounds__(kVoteThreads) k_probe_emit(EmitParams2 P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * kVoteThreads + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * kVoteThreads) >> 5;
+  unsigned long long cP = 0, cPf = 0, cE = 0, cQ = 0;
+  for (int64_t d = warp; d < P.nd; d += nwarps) {
+    const DescRec r = P.q[d];
+    const QAux a = P.aux[d];
+    const bool pass = (a.mask >> lane) & 1u;
+    uint32_t slot = 0, cnt = 0;
+    if (pass) {
+      const uint64_t key = probe_cell_key(r, lane);
+      uint64_t pos = mix64(key) & P.mask;
+      while (true) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.table[pos]));
+        const uint64_t k = ((uint64_t)raw.y << 32) | raw.x;
+        if (k == key) { slot = (uint32_t)pos; cnt = raw.w; break; }
+        if (k == SGTD_EMPTY_KEY) break;
+        pos = (pos + 1) & P.mask;
+      }
+    }
+    const unsigned m_pass = __ballot_sync(0xffffffffu, pass);
+    const unsigned m_found = __ballot_sync(0xffffffffu, cnt > 0);
+    uint32_t esum = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+    cQ += 1; cP += __popc(m_pass); cPf += __popc(m_found); cE += esum;
+    unsigned long long base = 0;
+    if (lane == 0 && m_found) base = atomicAdd(P.cursor, (unsigned long long)__popc(m_found));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (cnt > 0) {
+      const unsigned long long o = base + __popc(m_found & ((1u << lane) - 1u));
+      P.pkey[o] = slot | ((a.qi / P.group_div) << P.group_shift); P.pval[o] = (uint32_t)d;
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(P.counters + 0, cQ); atomicAdd(P.counters + 1, cP); atomicAdd(P.counters + 2, cPf);
+    atomicAdd(P.counters + 3, cE);
+  }
+}
+
+struct JoinParams {
+  const uint32_t *pkey, *pval;
+  unsigned long long npairs;
+  const DescRec *q; const QAux *aux;
+  const Bucket *table;
+  const double *s0, *s1, *s2; const uint32_t *fr;
+  uint32_t frame_lo; int64_t F;
+  uint32_t *votes;
+  unsigned long long *seg_counter, *counters;
+  uint32_t slot_mask;
+};
+
+template <bool kDoVote>
+__global__ void __launch_bounds__(kVoteThreads) k_vote_join(JoinParams P) {
+  __shared__ double sh_s[kVoteThreads / 32][kJoinSeg][4];    // s0, s1, s2, thr2 of each probe of the segment
+  __shared__ uint32_t sh_q[kVoteThreads / 32][kJoinSeg][2];  // query index, query frame id
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned long long nseg = (P.npairs + kJoinSeg - 1) / kJoinSeg;
+  unsigned long long cM = 0;
+  while (true) {
+    unsigned long long seg = 0;
+    if (lane == 0) seg = atomicAdd(P.seg_counter, 1ull);
+    seg = __shfl_sync(0xffffffffu, seg, 0);
+    if (seg >= nseg) break;
+    const unsigned long long p0 = seg * kJoinSeg;
+    const int np = (int)min((unsigned long long)kJoinSeg, P.npairs - p0);
+    uint32_t slot = 0xFFFFFFFFu;
+    __syncwarp();
+    if (lane < np) {
+      slot = P.pkey[p0 + lane];
+      const uint32_t d = P.pval[p0 + lane];
+      const DescRec r = P.q[d];
+      const QAux a = P.aux[d];
+      sh_s[wid][lane][0] = r.s[0]; sh_s[wid][lane][1] = r.s[1]; sh_s[wid][lane][2] = r.s[2]; sh_s[wid][lane][3] = a.thr2;
+      sh_q[wid][lane][0] = a.qi; sh_q[wid][lane][1] = r.frame;
+    }
+    __syncwarp();
+    int i = 0;
+    while (i < np) {
+      const uint32_t cur = __shfl_sync(0xffffffffu, slot, i);
+      const int run = __popc(__ballot_sync(0xffffffffu, slot == cur));  // sorted: equal slots are contiguous from i
+      const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.table[cur & P.slot_mask]));
+      const uint32_t o = raw.z, n = raw.w;
+      for (uint32_t e0 = 0; e0 < n; e0 += 32 * kVoteUnroll) {
+        double a[kVoteUnroll], b[kVoteUnroll], c[kVoteUnroll];
+        uint32_t f[kVoteUnroll];
+#pragma unroll
+        for (int u = 0; u < kVoteUnroll; ++u) {
+          const uint32_t e = e0 + 32 * u + lane;
+          const size_t idx = (size_t)o + (e < n ? e : n - 1);
+          a[u] = __ldg(P.s0 + idx); b[u] = __ldg(P.s1 + idx); c[u] = __ldg(P.s2 + idx);
+          f[u] = __ldg(P.fr + idx);
+        }
+        for (int p = i; p < i + run; ++p) {
+          const double q0 = sh_s[wid][p][0], q1 = sh_s[wid][p][1], q2 = sh_s[wid][p][2], thr2 = sh_s[wid][p][3];
+          const uint32_t qframe = sh_q[wid][p][1];
+          uint32_t *row = P.votes + (size_t)sh_q[wid][p][0] * (size_t)P.F;
+#pragma unroll
+          for (int u = 0; u < kVoteUnroll; ++u) {
+            const uint32_t e = e0 + 32 * u + lane;
+            const double d2 = sqn3(__dsub_rn(q0, a[u]), __dsub_rn(q1, b[u]), __dsub_rn(q2, c[u]));
+            const bool hit = (e < n) && (f[u] + P.frame_lo != qframe) && (d2 < thr2);
+            if (kDoVote && hit) atomicAdd(row + f[u], 1u);
+            cM += hit;
+          }
+        }
+      }
+      i += run;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cM += __shfl_xor_sync(0xffffffffu, cM, o);
+  if (lane == 0 && cM) atomicAdd(P.counters + 4, cM);
 }
 
 // ============================ top-k ==============================================
@@ -302,37 +483,41 @@ constexpr int kSmemKeys = 4096;
 struct CollectParams {
   const sgtd_candidate *cands;
   int k;
-  const DescRec *q; const int64_t *q_off;
+  const DescRec *q; const QAux *aux; const int64_t *q_off;
   const DescRec *db; const int64_t *frame_off; const uint64_t *f_key; const uint32_t *f_g;
   int64_t frame_lo;
-  double rough;
   uint32_t *m_q, *m_g; uint8_t *m_cell;
 };
 
 // matches of query descriptor r against keyframe view keys[0..nf): calls emit(ord, g)
+// in (probe ordinal, in-frame position) order
 template <typename Emit>
-__device__ __forceinline__ void desc_vs_frame(const DescRec &r, const uint64_t *keys, int nf, const uint32_t *fg,
-                                              const DescRec *db, double rough, Emit emit) {
-  const double thr2 = sq_threshold(__dmul_rn(norm3(r.s[0], r.s[1], r.s[2]), rough));
-  for (int ord = 0; ord < 27; ++ord) {
-    uint64_t key;
-    if (!probe_key(r, ord, key)) continue;
+__device__ __forceinline__ void desc_vs_frame(const DescRec &r, const QAux &a, const uint64_t *keys, int nf,
+                                              const uint32_t *fg, const DescRec *db, Emit emit) {
+  uint32_t m = a.mask;
+  while (m) {
+    const int ord = __ffs(m) - 1;
+    m &= m - 1;
+    const uint64_t key = probe_cell_key(r, ord);
     int lo = 0, hi = nf;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
     for (int p = lo; p < nf && keys[p] == key; ++p) {
       const uint32_t g = fg[p];
       const DescRec e = db[g];
       if (e.frame == r.frame) continue;
       const double d2 = sqn3(__dsub_rn(r.s[0], e.s[0]), __dsub_rn(r.s[1], e.s[1]), __dsub_rn(r.s[2], e.s[2]));
-      if (d2 < thr2) emit(ord, g);
+      if (d2 < a.thr2) emit(ord, g);
     }
   }
 }
 
 // One CTA per (query, candidate keyframe): the keyframe's key-sorted view sits in
-// shared memory; each thread joins one query descriptor against it (27 binary
-// searches); a block scan turns per-descriptor counts into the reference's
-// (descriptor, probe ordinal, bucket position) order.
+// shared memory; each thread joins one query descriptor against it (one binary
+// search per probe that passed the ball test); the first matches of a descriptor are
+// kept in registers, a block scan turns per-descriptor counts into the reference's
+// (descriptor, probe ordinal, bucket position) order, and only descriptors with more
+// matches than the register buffer walk the view a second time.
+constexpr int kCollectBuf = 4;
 __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
   __shared__ uint64_t s_keys[kSmemKeys];
   __shared__ uint32_t s_warp[kCollectThreads / 32];
@@ -356,10 +541,15 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
   for (int64_t i0 = q0; i0 < q1; i0 += kCollectThreads) {
     const int64_t i = i0 + tid;
     uint32_t cnt = 0;
-    DescRec r;
+    uint32_t bg[kCollectBuf]; uint8_t bo[kCollectBuf];
+    DescRec r; QAux a;
     if (i < q1) {
-      r = P.q[i];
-      desc_vs_frame(r, keys, nf, fg, P.db, P.rough, [&](int, uint32_t) { ++cnt; });
+      r = P.q[i]; a = P.aux[i];
+      desc_vs_frame(r, a, keys, nf, fg, P.db, [&](int ord, uint32_t g) {
+#pragma unroll
+        for (int b = 0; b < kCollectBuf; ++b) if (cnt == (uint32_t)b) { bg[b] = g; bo[b] = (uint8_t)ord; }
+        ++cnt;
+      });
     }
     // block exclusive scan of cnt
     uint32_t incl = cnt;
@@ -374,10 +564,16 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
     if (cnt) {
       int64_t pos = base + wbase + incl - cnt;
       const uint32_t qi = (uint32_t)(i - q0);
-      desc_vs_frame(r, keys, nf, fg, P.db, P.rough, [&](int ord, uint32_t g) {
-        if (pos < limit) { P.m_q[pos] = qi; P.m_cell[pos] = (uint8_t)ord; P.m_g[pos] = g; }
-        ++pos;
-      });
+      if (cnt <= (uint32_t)kCollectBuf) {
+#pragma unroll
+        for (int b = 0; b < kCollectBuf; ++b)
+          if ((uint32_t)b < cnt && pos + b < limit) { P.m_q[pos + b] = qi; P.m_cell[pos + b] = bo[b]; P.m_g[pos + b] = bg[b]; }
+      } else {
+        desc_vs_frame(r, a, keys, nf, fg, P.db, [&](int ord, uint32_t g) {
+          if (pos < limit) { P.m_q[pos] = qi; P.m_cell[pos] = (uint8_t)ord; P.m_g[pos] = g; }
+          ++pos;
+        });
+      }
     }
     base += total;
   }
@@ -583,9 +779,34 @@ __device__ __forceinline__ void load_pair(const VerifyParams &P, int64_t q0, int
 // the 3-point Kabsch of pair h*skip and keeps (R,t) in registers.  Match pairs
 // are staged 64 at a time in shared memory; every hypothesis thread walks the
 // tile with broadcast reads, so each pair is fetched from HBM/L2 once per pass.
+//
+// Hypothesis votes use an FP32 pre-filter: the residual of each vertex is first formed
+// in float (FMA).  With |coordinate|, |t| <= X the float residual components are off by
+// at most ~40*eps32*X, so the squared residual is off by < 16*40*eps32*X near the 3 m
+// boundary; outside the band 9 +- margin(X) the float decision equals the reference's
+// FP64 decision, inside it the vertex is re-evaluated exactly in FP64.  Outcomes are
+// therefore identical to pair_inlier() for every pair (checked bit-for-bit by the tests).
+struct __align__(16) PairTile {  // 20 floats: A,B,C of the query, A',B',C' of the keyframe, max |coord|, pad
+  float4 v[5];
+};
+__device__ __forceinline__ bool vertex_inlier_fast(const float *Rf, const float *tf, const double *R, const double *t,
+                                                   float px, float py, float pz, float bx, float by, float bz,
+                                                   float margin) {
+  const float rx = fmaf(Rf[0], px, fmaf(Rf[1], py, fmaf(Rf[2], pz, tf[0]))) - bx;
+  const float ry = fmaf(Rf[3], px, fmaf(Rf[4], py, fmaf(Rf[5], pz, tf[1]))) - by;
+  const float rz = fmaf(Rf[6], px, fmaf(Rf[7], py, fmaf(Rf[8], pz, tf[2]))) - bz;
+  const float d2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+  if (d2 < 9.0f - margin) return true;
+  if (d2 > 9.0f + margin) return false;
+  // ambiguous: exact FP64 evaluation in the reference's operation order
+  const double dx = __dsub_rn(__dadd_rn(dot3s(R[0], (double)px, R[1], (double)py, R[2], (double)pz), t[0]), (double)bx);
+  const double dy = __dsub_rn(__dadd_rn(dot3s(R[3], (double)px, R[4], (double)py, R[5], (double)pz), t[1]), (double)by);
+  const double dz = __dsub_rn(__dadd_rn(dot3s(R[6], (double)px, R[7], (double)py, R[8], (double)pz), t[2]), (double)bz);
+  return sqn3(dx, dy, dz) < 9.0;
+}
+
 __global__ void __launch_bounds__(kVerifyThreads) k_verify(VerifyParams P) {
-  __shared__ float s_a[kVerifyThreads][9];
-  __shared__ float s_b[kVerifyThreads][9];
+  __shared__ PairTile s_pair[kVerifyThreads];
   __shared__ int s_vote[kVerifyThreads];
   __shared__ double s_pose[12];
   __shared__ int s_best, s_wcnt[2];
@@ -604,14 +825,39 @@ __global__ void __launch_bounds__(kVerifyThreads) k_verify(VerifyParams P) {
     load_pair(P, q0, moff + (int64_t)tid * skip, a, b);
     kabsch3(a, b, R, t);
   }
+  float Rf[9], tf[3], tmax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Rf[i] = (tid < H) ? (float)R[i] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { tf[i] = (tid < H) ? (float)t[i] : 0.f; tmax = fmaxf(tmax, fabsf(tf[i])); }
   int vote = 0;
   for (int jb = 0; jb < M; jb += kVerifyThreads) {
     const int nt = min(kVerifyThreads, M - jb);
     __syncthreads();
-    if (tid < nt) load_pair(P, q0, moff + jb + tid, s_a[tid], s_b[tid]);
+    if (tid < nt) {
+      float a[9], b[9];
+      load_pair(P, q0, moff + jb + tid, a, b);
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) mx = fmaxf(mx, fmaxf(fabsf(a[i]), fabsf(b[i])));
+      PairTile pt;
+      pt.v[0] = make_float4(a[0], a[1], a[2], a[3]); pt.v[1] = make_float4(a[4], a[5], a[6], a[7]);
+      pt.v[2] = make_float4(a[8], b[0], b[1], b[2]); pt.v[3] = make_float4(b[3], b[4], b[5], b[6]);
+      pt.v[4] = make_float4(b[7], b[8], mx, 0.f);
+      s_pair[tid] = pt;
+    }
     __syncthreads();
     if (tid < H)
-      for (int jj = 0; jj < nt; ++jj) vote += pair_inlier(R, t, s_a[jj], s_b[jj]);
+      for (int jj = 0; jj < nt; ++jj) {
+        const float4 v0 = s_pair[jj].v[0], v1 = s_pair[jj].v[1], v2 = s_pair[jj].v[2], v3 = s_pair[jj].v[3],
+                     v4 = s_pair[jj].v[4];
+        // margin(X) = 16 * 40 * eps32 * X (+ slack), X = max |coordinate| of the pair and |t|
+        const float margin = fminf(fmaf(4.0e-5f, fmaxf(v4.z, tmax), 1.0e-4f), 8.0f);
+        const bool ok = vertex_inlier_fast(Rf, tf, R, t, v0.x, v0.y, v0.z, v2.y, v2.z, v2.w, margin) &&
+                        vertex_inlier_fast(Rf, tf, R, t, v0.w, v1.x, v1.y, v3.x, v3.y, v3.z, margin) &&
+                        vertex_inlier_fast(Rf, tf, R, t, v1.z, v1.w, v2.x, v3.w, v4.x, v4.y, margin);
+        vote += ok;
+      }
   }
   s_vote[tid] = (tid < H) ? vote : -1;
   __syncthreads();
@@ -730,28 +976,107 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   size_t o_off = o; o += al((nslot + 1) * 8);
   size_t o_cub = o; o += al(cubb);
   size_t o_gc = o; o += (h->nranks > 1) ? al(nslot * sizeof(sgtd_candidate) * h->nranks) : 0;
+  size_t o_aux = o; o += al((size_t)std::max<int64_t>(qb->n, 1) * sizeof(QAux));
+  // vote formulation: bucket-major join (default) or per-probe streaming (SGTD_VOTE_MODE=stream)
+  const char *vmode = getenv("SGTD_VOTE_MODE");
+  const bool join_mode = !(vmode && strcmp(vmode, "stream") == 0) && qb->n > 0 && h->rec.n > 0;
+  bool join_timed = false;
+  const bool sort_q = !join_mode && qb->n > 0;  // streaming mode walks descriptors in cell-key order (L2 reuse)
+  size_t cubj = 0;
+  const size_t npair_cap = join_mode ? (size_t)qb->n * 27 : 0;
+  if (join_mode) cub::DeviceRadixSort::SortPairs(nullptr, cubj, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)npair_cap, 0, 32, st);
+  size_t cubs = 0;
+  if (sort_q) cub::DeviceRadixSort::SortPairs(nullptr, cubs, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, qb->n, 0, 60, st);
+  size_t o_sk0 = o; o += sort_q ? al(qb->n * 8) : 0;
+  size_t o_sk1 = o; o += sort_q ? al(qb->n * 8) : 0;
+  size_t o_si0 = o; o += sort_q ? al(qb->n * 4) : 0;
+  size_t o_si1 = o; o += sort_q ? al(qb->n * 4) : 0;
+  size_t o_cubs = o; o += al(cubs);
+  size_t o_jk0 = o; o += al(npair_cap * 4);
+  size_t o_jk1 = o; o += al(npair_cap * 4);
+  size_t o_jv0 = o; o += al(npair_cap * 4);
+  size_t o_jv1 = o; o += al(npair_cap * 4);
+  size_t o_jc = o; o += al(64);
+  size_t o_jcub = o; o += al(cubj);
   SGTD_CUDA(h, h->scratch.reserve(o, st, false));
   unsigned char *S = h->scratch.p;
   int32_t *lv = (int32_t *)(S + o_lv), *lf = (int32_t *)(S + o_lf), *gv = (int32_t *)(S + o_gv), *gf = (int32_t *)(S + o_gf);
   int32_t *mv = (int32_t *)(S + o_mv), *mf = (int32_t *)(S + o_mf);
   int64_t *cnt = (int64_t *)(S + o_cnt), *off = (int64_t *)(S + o_off);
 
+  QAux *aux = (QAux *)(S + o_aux);
   SGTD_CUDA(h, cudaEventRecord(ev[0], st));
+  if (qb->n > 0) {
+    k_qaux<<<(unsigned)((qb->n + 255) / 256), 256, 0, st>>>(qb->rec.p, qb->d_off.p, nq, qb->n, h->c.rough, aux,
+                                                             sort_q ? (uint64_t *)(S + o_sk0) : nullptr, (uint32_t *)(S + o_si0));
+    SGTD_LAUNCHED(h);
+    if (sort_q) {
+      SGTD_CUDA(h, cub::DeviceRadixSort::SortPairs(S + o_cubs, cubs, (uint64_t *)(S + o_sk0), (uint64_t *)(S + o_sk1),
+                                                   (uint32_t *)(S + o_si0), (uint32_t *)(S + o_si1), qb->n, 0, 60, st));
+      SGTD_LAUNCHED(h);
+    }
+  }
   SGTD_CUDA(h, cudaMemsetAsync(r->votes.p, 0, (size_t)nq * Fa * 4, st));
   SGTD_CUDA(h, cudaMemsetAsync(r->counters.p, 0, 8 * 8, st));
   SGTD_CUDA(h, cudaEventRecord(ev[7], st));
   if (nq > 0 && qb->n > 0 && h->rec.n > 0) {
     VoteParams V{};
-    V.q = qb->rec.p; V.q_off = qb->d_off.p; V.nq = nq; V.nd = qb->n;
+    V.perm = sort_q ? (const uint32_t *)(S + o_si1) : nullptr;
+    V.q = qb->rec.p; V.aux = aux; V.q_off = qb->d_off.p; V.nq = nq; V.nd = qb->n;
     V.table = h->table.p; V.mask = h->table_mask;
     V.s0 = h->v_s0.p; V.s1 = h->v_s1.p; V.s2 = h->v_s2.p; V.fr = h->v_frame.p;
     V.frame_lo = (uint32_t)h->frame_lo(); V.F = Fa; V.rough = h->c.rough;
     V.votes = r->votes.p; V.counters = r->counters.p;
     const int64_t warps_needed = qb->n;
     int grid = (int)std::min<int64_t>((warps_needed * 32 + kVoteThreads - 1) / kVoteThreads, (int64_t)h->sm_count * 8);
-    k_vote<<<grid, kVoteThreads, 0, st>>>(V);
-    SGTD_LAUNCHED(h);
-    SGTD_CUDA(h, cudaGetLastError());
+    if (!join_mode) {
+      if (getenv("SGTD_DEBUG_NOVOTE")) k_vote<false><<<grid, kVoteThreads, 0, st>>>(V);
+      else k_vote<true><<<grid, kVoteThreads, 0, st>>>(V);
+      SGTD_LAUNCHED(h);
+      SGTD_CUDA(h, cudaGetLastError());
+    } else {
+      unsigned long long *d_cursor = (unsigned long long *)(S + o_jc);
+      SGTD_CUDA(h, cudaMemsetAsync(d_cursor, 0, 16, st));
+      EmitParams2 E2{};
+      E2.q = qb->rec.p; E2.aux = aux; E2.nd = qb->n; E2.table = h->table.p; E2.mask = h->table_mask;
+      E2.pkey = (uint32_t *)(S + o_jk0); E2.pval = (uint32_t *)(S + o_jv0);
+      E2.cursor = d_cursor; E2.counters = r->counters.p;
+      int sbits = 1;
+      while ((1ull << sbits) <= h->table_mask) ++sbits;
+      // Probes are processed query-group by query-group so that the vote rows being reduced into
+      // (nq/ngroups x F x 4 B) stay L2-resident (~96 MB of the 126 MB L2); more groups = fewer probes
+      // per bucket run, so no more than needed.
+      int ngroups = (int)std::min<int64_t>(16, std::max<int64_t>(1, ((int64_t)nq * Fa * 4 + (96ll << 20) - 1) / (96ll << 20)));
+      if (getenv("SGTD_JOIN_GROUPS")) ngroups = std::max(1, atoi(getenv("SGTD_JOIN_GROUPS")));
+      E2.group_shift = (uint32_t)sbits; E2.group_div = (uint32_t)std::max(1, (nq + ngroups - 1) / ngroups);
+      int gbits = 0;
+      while ((1 << gbits) < ngroups) ++gbits;
+      k_probe_emit<<<grid, kVoteThreads, 0, st>>>(E2);
+      SGTD_LAUNCHED(h);
+      unsigned long long npairs = 0;
+      SGTD_CUDA(h, cudaMemcpyAsync(&npairs, d_cursor, 8, cudaMemcpyDeviceToHost, st));
+      SGTD_CUDA(h, cudaStreamSynchronize(st));
+      if (npairs > 0) {
+        const int bits = std::min(32, sbits + gbits);
+        size_t tmp = cubj;
+        SGTD_CUDA(h, cub::DeviceRadixSort::SortPairs(S + o_jcub, tmp, (uint32_t *)(S + o_jk0), (uint32_t *)(S + o_jk1),
+                                                     (uint32_t *)(S + o_jv0), (uint32_t *)(S + o_jv1), (int64_t)npairs, 0, bits, st));
+        SGTD_LAUNCHED(h);
+        JoinParams J{};
+        J.pkey = (uint32_t *)(S + o_jk1); J.pval = (uint32_t *)(S + o_jv1); J.npairs = npairs;
+        J.q = qb->rec.p; J.aux = aux; J.table = h->table.p;
+        J.s0 = h->v_s0.p; J.s1 = h->v_s1.p; J.s2 = h->v_s2.p; J.fr = h->v_frame.p;
+        J.frame_lo = (uint32_t)h->frame_lo(); J.F = Fa; J.votes = r->votes.p;
+        J.seg_counter = d_cursor + 1; J.counters = r->counters.p; J.slot_mask = (uint32_t)((1ull << sbits) - 1);
+        SGTD_CUDA(h, cudaEventRecord(ev[8], st));
+        const int jgrid = h->sm_count * 4;
+        if (getenv("SGTD_DEBUG_NOVOTE")) k_vote_join<false><<<jgrid, kVoteThreads, 0, st>>>(J);
+        else k_vote_join<true><<<jgrid, kVoteThreads, 0, st>>>(J);
+        SGTD_LAUNCHED(h);
+        SGTD_CUDA(h, cudaGetLastError());
+        join_timed = true;
+      }
+    }
   }
   SGTD_CUDA(h, cudaEventRecord(ev[1], st));
   const int vote_launches = (int)(h->launches - launches0);
@@ -792,9 +1117,9 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   r->m_q.n = r->m_g.n = r->m_cell.n = r->inl.n = (size_t)total;
   if (total > 0) {
     CollectParams C{};
-    C.cands = r->cands.p; C.k = k; C.q = qb->rec.p; C.q_off = qb->d_off.p;
+    C.cands = r->cands.p; C.k = k; C.q = qb->rec.p; C.aux = aux; C.q_off = qb->d_off.p;
     C.db = h->rec.p; C.frame_off = h->d_frame_off.p; C.f_key = h->f_key.p; C.f_g = h->f_g.p;
-    C.frame_lo = h->frame_lo(); C.rough = h->c.rough;
+    C.frame_lo = h->frame_lo();
     C.m_q = r->m_q.p; C.m_g = r->m_g.p; C.m_cell = r->m_cell.p;
     k_collect<<<(unsigned)nslot, kCollectThreads, 0, st>>>(C);
     SGTD_LAUNCHED(h);
@@ -829,7 +1154,8 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   SGTD_CUDA(h, cudaEventRecord(ev[6], st));
   SGTD_CUDA(h, cudaStreamSynchronize(st));
   r->tm.clear_ms = ev_ms(ev[0], ev[7]);
-  r->tm.vote_ms = ev_ms(ev[7], ev[1]);
+  r->tm.vote_ms = join_timed ? ev_ms(ev[8], ev[1]) : ev_ms(ev[7], ev[1]);
+  r->tm.probe_ms = join_timed ? ev_ms(ev[7], ev[8]) : 0.f;
   r->tm.topk_ms = ev_ms(ev[1], ev[2]);
   r->tm.exchange_ms = ev_ms(ev[2], ev[3]);
   r->tm.collect_ms = ev_ms(ev[3], ev[4]);
