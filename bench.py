@@ -321,10 +321,33 @@ def run_ours(args):
         # success in the reference's sense needs poses; here: best keyframe within 10 m of the true place
         P = cfg["world"]["poses"]
         ok = 0
+        # the reference's success criterion (semantic_graph_localization.cpp:724-750, compute_adj_rpe
+        # utility.hpp:110-123): T_est = T_map[match] * [R|t]_loop against the query's true pose,
+        # success iff translation error < 5 m and rotation error < 10 deg
+        cands_h = np.frombuffer(cands_pin.numpy().tobytes(), capi.CAND_DTYPE).reshape(nq, k)
+
+        def se3(pose):
+            c, s_ = np.cos(pose[2]), np.sin(pose[2])
+            T = np.eye(4)
+            T[:2, :2] = [[c, -s_], [s_, c]]
+            T[:2, 3] = pose[:2]
+            return T
+        succ, terr, rerr = 0, [], []
         for qi in range(nq):
             f = loops["frame"][qi]
-            if f >= 0 and np.hypot(*(P[f, :2] - cfg["qposes"][qi, :2])) < 10.0:
+            if f < 0:
+                continue
+            if np.hypot(*(P[f, :2] - cfg["qposes"][qi, :2])) < 10.0:
                 ok += 1
+            c = [c for c in cands_h[qi] if c["frame"] == f and c["score"] == loops["score"][qi]][0]
+            Tl = np.eye(4)
+            Tl[:3, :3] = c["R"].reshape(3, 3)
+            Tl[:3, 3] = c["t"]
+            d = np.linalg.inv(se3(P[f]) @ Tl) @ se3(cfg["qposes"][qi])
+            te = float(np.linalg.norm(d[:3, 3]))
+            re = float(np.degrees(np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1))))
+            terr.append(te); rerr.append(re)
+            succ += te < 5.0 and re < 10.0
         line = {
             "metric": METRIC, "value": nq * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -344,7 +367,9 @@ def run_ours(args):
                          "traffic_frac_of_peak": (traffic / (vms * 1e-3) / 1e9 / peak) if traffic else None,
                          "note": ROOFLINE_NOTE},
             "stage_ms": {kk: round(vv, 3) for kk, vv in stage.items()},
-            "recall": {"found": found, "within_10m": ok, "queries": nq},
+            "recall": {"found": found, "within_10m": ok, "queries": nq, "success_T5m_R10deg": int(succ),
+                       "rmse_t_m": float(np.sqrt(np.mean(np.square(terr)))) if terr else None,
+                       "rmse_r_deg": float(np.sqrt(np.mean(np.square(rerr)))) if rerr else None},
             # checksum of (best frame, score, candidate frames/votes/scores): identical for every N
             "result_crc": result_crc(loops, np.frombuffer(cands_pin.numpy().tobytes(), capi.CAND_DTYPE)),
             "clocks": clocks,

@@ -115,6 +115,31 @@ def test_search_parity(world, built):
     assert stats == tot
 
 
+def test_vote_formulations_agree(world, built, monkeypatch):
+    """The bucket-major join (default), the per-probe streaming kernel (SGTD_VOTE_MODE=stream) and
+    the join with several query groups give identical votes, counters and candidates."""
+    mgr, o, *_ = built
+    qx, ql, qo = world["queries"]
+    qb = mgr.build(capi.make_nodes(qx, ql), qo)
+    F = o.current_frame_id
+    ref = None
+    for env in ({}, {"SGTD_VOTE_MODE": "stream"}, {"SGTD_JOIN_GROUPS": "3"}):
+        for k in ("SGTD_VOTE_MODE", "SGTD_JOIN_GROUPS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        res = mgr.search(qb)
+        loops, cands = res.download()
+        stats, _ = res.stats()
+        votes = np.stack([res.votes(q, F) for q in range(qo.shape[0] - 1)])
+        cur = (votes.tobytes(), loops.tobytes(), cands.tobytes(), stats)
+        if ref is None:
+            ref = cur
+        else:
+            assert cur[0] == ref[0] and cur[1] == ref[1] and cur[3] == ref[3]
+            assert cur[2] == ref[2]
+
+
 def test_single_scan_facade_flow(world, oracle_lib):
     """Build/Add one keyframe at a time, as semantic_graph_localization.cpp:419-495 does."""
     xyz, lab, off = world["db"]
