@@ -256,6 +256,21 @@ int sgtd_extract_instances_batch(sgtd_handle *h, const float *points,
                                  int64_t cap_nodes, int64_t *node_offsets,
                                  int32_t *n_instances);
 
+/* ---- file formats either side of the path (host only) --------------------------- */
+/* Graph JSON of one scan, wire-compatible with Graph::toJSON / fromJSON
+ * (R/include/Semantic_Graph.hpp:79-157): keys nodes, centers, poses (+ the empty edges,
+ * weights, volumes, densitys).  poses12 = row-major 3x4 pose, may be NULL on write. */
+int sgtd_graph_write_json(const char *path, const sgtd_node *nodes,
+                          int32_t n_nodes, const float *poses12);
+/* readGraphFromFile + Graph2CloudL (R/include/Semantic_Graph.hpp:169-184,
+ * R/include/utility.hpp:646-659).  *n_nodes is set even on SGTD_E_CAPACITY. */
+int sgtd_graph_read_json(const char *path, sgtd_node *nodes, int32_t cap,
+                         int32_t *n_nodes, float *poses12, int32_t *n_poses);
+/* KITTI .bin (float32 x,y,z,i) + .label (uint32) as gen_labels reads them
+ * (R/src/get_json.cpp:47-84).  points/labels may be NULL to query *n. */
+int sgtd_scan_read_kitti(const char *bin_path, const char *label_path,
+                         float *points, uint32_t *labels, int64_t cap, int64_t *n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,9 @@ SYMBOLS = {
     "sgtd_shard_init": (C.c_int, [_VP, _I32, _I32, _I64, _VP]),
     "sgtd_extract_instances": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _VP, _I32, _VP, _VP]),
     "sgtd_extract_instances_batch": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP, _VP, _I64, _VP, _VP]),
+    "sgtd_graph_write_json": (C.c_int, [C.c_char_p, _VP, _I32, _VP]),
+    "sgtd_graph_read_json": (C.c_int, [C.c_char_p, _VP, _I32, _VP, _VP, _VP]),
+    "sgtd_scan_read_kitti": (C.c_int, [C.c_char_p, C.c_char_p, _VP, _VP, _I64, _VP]),
 }
 
 _lib = None
@@ -355,6 +358,41 @@ class STDescManager:
         self._chk(lib().sgtd_extract_instances_batch(self._h, _p(points), _p(labels), _p(offsets), ns, _p(pi),
                                                      _p(nodes), cap, _p(noff), _p(ninst)))
         return nodes[:noff[ns]].copy(), noff, pi, ninst[:ns]
+
+
+def graph_write_json(path, nodes, poses12=None):
+    nodes = np.ascontiguousarray(nodes, NODE_DTYPE)
+    p = None if poses12 is None else np.ascontiguousarray(poses12, np.float32).reshape(12)
+    rc = lib().sgtd_graph_write_json(path.encode(), _p(nodes), nodes.shape[0], _p(p))
+    if rc:
+        raise SgtdError(rc, f"cannot write {path}")
+
+
+def graph_read_json(path):
+    """-> (nodes NODE_DTYPE[k], poses float32[<=12])"""
+    n, npz = C.c_int32(0), C.c_int32(0)
+    poses = np.zeros(12, np.float32)
+    rc = lib().sgtd_graph_read_json(path.encode(), None, 0, C.byref(n), _p(poses), C.byref(npz))
+    if rc not in (OK, E_CAPACITY):
+        raise SgtdError(rc, f"cannot read {path}")
+    nodes = np.zeros(max(n.value, 1), NODE_DTYPE)
+    rc = lib().sgtd_graph_read_json(path.encode(), _p(nodes), n.value, C.byref(n), _p(poses), C.byref(npz))
+    if rc:
+        raise SgtdError(rc, f"cannot read {path}")
+    return nodes[:n.value], poses[:min(npz.value, 12)]
+
+
+def scan_read_kitti(bin_path, label_path):
+    n = C.c_int64(0)
+    rc = lib().sgtd_scan_read_kitti(bin_path.encode(), None, None, None, 0, C.byref(n))
+    if rc:
+        raise SgtdError(rc, f"cannot read {bin_path}")
+    pts = np.zeros((n.value, 4), np.float32)
+    lab = np.zeros(n.value, np.uint32)
+    rc = lib().sgtd_scan_read_kitti(bin_path.encode(), label_path.encode(), _p(pts), _p(lab), n.value, C.byref(n))
+    if rc:
+        raise SgtdError(rc, f"cannot read {label_path}")
+    return pts, lab
 
 
 def nccl_unique_id():

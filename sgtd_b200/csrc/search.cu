@@ -491,17 +491,51 @@ struct CollectParams {
 
 // matches of query descriptor r against keyframe view keys[0..nf): calls emit(ord, g)
 // in (probe ordinal, in-frame position) order
+// Where the entries with a given key start inside a keyframe's key-sorted view.
+//  * view in shared memory: a radix start table over the top bits of (key - kmin) narrows the
+//    range to a handful of entries (two table reads + a short linear scan);
+//  * view too large for shared memory: plain binary search in global memory.
+constexpr int kBins = 4096;
+struct KeyFinder {
+  const uint64_t *keys; int nf;
+  const uint16_t *start;  // kBins + 1 entries or nullptr
+  int xmin, xmax, ymin, ymax, ny;  // bins = (x - xmin) * ny + (y - ymin): monotone in the (x,y,z,code)-sorted view
+  __device__ __forceinline__ int lower_bound(uint64_t key, int &end) const {
+    int lo = 0, hi = nf;
+    if (start) {
+      const int x = (int)(key >> 44), y = (int)((key >> 28) & 0xFFFF);
+      if (x < xmin || x > xmax || y < ymin || y > ymax) { end = 0; return 0; }
+      const int b = (x - xmin) * ny + (y - ymin);
+      lo = start[b]; hi = start[b + 1];
+    }
+    end = hi;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+  }
+};
+
+// matches of query descriptor r against a keyframe view: calls emit(ord, g) in
+// (probe ordinal, in-frame position) order
 template <typename Emit>
-__device__ __forceinline__ void desc_vs_frame(const DescRec &r, const QAux &a, const uint64_t *keys, int nf,
+__device__ __forceinline__ void desc_vs_frame(const DescRec &r, const QAux &a, const KeyFinder &kf,
                                               const uint32_t *fg, const DescRec *db, Emit emit) {
+  // (int)(side + inc) for inc = -1, 0, +1, once per descriptor
+  uint32_t cx[3], cy[3], cz[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    cx[k] = (uint32_t)__double2int_rz(__dadd_rn(r.s[0], (double)(k - 1)));
+    cy[k] = (uint32_t)__double2int_rz(__dadd_rn(r.s[1], (double)(k - 1)));
+    cz[k] = (uint32_t)__double2int_rz(__dadd_rn(r.s[2], (double)(k - 1)));
+  }
   uint32_t m = a.mask;
   while (m) {
     const int ord = __ffs(m) - 1;
     m &= m - 1;
-    const uint64_t key = probe_cell_key(r, ord);
-    int lo = 0, hi = nf;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
-    for (int p = lo; p < nf && keys[p] == key; ++p) {
+    const int ox = ord / 9, oy = (ord / 3) % 3, oz = ord % 3;
+    const uint64_t key = pack_key(ox == 0 ? cx[0] : (ox == 1 ? cx[1] : cx[2]), oy == 0 ? cy[0] : (oy == 1 ? cy[1] : cy[2]),
+                                  oz == 0 ? cz[0] : (oz == 1 ? cz[1] : cz[2]), r.code);
+    int end;
+    for (int p = kf.lower_bound(key, end); p < end && kf.keys[p] == key; ++p) {
       const uint32_t g = fg[p];
       const DescRec e = db[g];
       if (e.frame == r.frame) continue;
@@ -520,6 +554,8 @@ __device__ __forceinline__ void desc_vs_frame(const DescRec &r, const QAux &a, c
 constexpr int kCollectBuf = 4;
 __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
   __shared__ uint64_t s_keys[kSmemKeys];
+  __shared__ uint16_t s_start[kBins + 1];
+  __shared__ int s_yr[2];
   __shared__ uint32_t s_warp[kCollectThreads / 32];
   const sgtd_candidate c = P.cands[blockIdx.x];
   if (c.match_off < 0 || c.nmatch <= 0) return;
@@ -528,10 +564,36 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
   const int64_t fl = c.frame - P.frame_lo;
   const int64_t fo = P.frame_off[fl];
   const int nf = (int)(P.frame_off[fl + 1] - fo);
-  const uint64_t *keys = P.f_key + fo;
-  if (nf <= kSmemKeys) {
-    for (int i = tid; i < nf; i += kCollectThreads) s_keys[i] = keys[i];
-    keys = s_keys;
+  KeyFinder kf;
+  kf.keys = P.f_key + fo; kf.nf = nf; kf.start = nullptr; kf.xmin = kf.xmax = kf.ymin = kf.ymax = 0; kf.ny = 1;
+  if (nf > 0 && nf <= kSmemKeys) {
+    if (tid == 0) { s_yr[0] = 0x7fffffff; s_yr[1] = -1; }
+    __syncthreads();
+    int ylo = 0x7fffffff, yhi = -1;
+    for (int i = tid; i < nf; i += kCollectThreads) {
+      const uint64_t kk = kf.keys[i];
+      s_keys[i] = kk;
+      const int y = (int)((kk >> 28) & 0xFFFF);
+      ylo = min(ylo, y); yhi = max(yhi, y);
+    }
+    if (yhi >= 0) { atomicMin(&s_yr[0], ylo); atomicMax(&s_yr[1], yhi); }
+    __syncthreads();
+    kf.keys = s_keys;
+    kf.xmin = (int)(s_keys[0] >> 44); kf.xmax = (int)(s_keys[nf - 1] >> 44);
+    kf.ymin = s_yr[0]; kf.ymax = s_yr[1]; kf.ny = kf.ymax - kf.ymin + 1;
+    if ((long long)(kf.xmax - kf.xmin + 1) * kf.ny <= kBins) {
+      // start[b] = first index whose bin is >= b
+      const int nb = (kf.xmax - kf.xmin + 1) * kf.ny;
+      for (int i = tid; i < nf; i += kCollectThreads) {
+        const uint64_t k1 = s_keys[i];
+        const int bi = ((int)(k1 >> 44) - kf.xmin) * kf.ny + ((int)((k1 >> 28) & 0xFFFF) - kf.ymin);
+        int bp = -1;
+        if (i) { const uint64_t k0 = s_keys[i - 1]; bp = ((int)(k0 >> 44) - kf.xmin) * kf.ny + ((int)((k0 >> 28) & 0xFFFF) - kf.ymin); }
+        for (int b = bp + 1; b <= bi; ++b) s_start[b] = (uint16_t)i;
+        if (i == nf - 1) for (int b = bi + 1; b <= nb; ++b) s_start[b] = (uint16_t)nf;
+      }
+      kf.start = s_start;
+    }
   }
   __syncthreads();
   const uint32_t *fg = P.f_g + fo;
@@ -545,7 +607,7 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
     DescRec r; QAux a;
     if (i < q1) {
       r = P.q[i]; a = P.aux[i];
-      desc_vs_frame(r, a, keys, nf, fg, P.db, [&](int ord, uint32_t g) {
+      desc_vs_frame(r, a, kf, fg, P.db, [&](int ord, uint32_t g) {
 #pragma unroll
         for (int b = 0; b < kCollectBuf; ++b) if (cnt == (uint32_t)b) { bg[b] = g; bo[b] = (uint8_t)ord; }
         ++cnt;
@@ -569,7 +631,7 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
         for (int b = 0; b < kCollectBuf; ++b)
           if ((uint32_t)b < cnt && pos + b < limit) { P.m_q[pos + b] = qi; P.m_cell[pos + b] = bo[b]; P.m_g[pos + b] = bg[b]; }
       } else {
-        desc_vs_frame(r, a, keys, nf, fg, P.db, [&](int ord, uint32_t g) {
+        desc_vs_frame(r, a, kf, fg, P.db, [&](int ord, uint32_t g) {
           if (pos < limit) { P.m_q[pos] = qi; P.m_cell[pos] = (uint8_t)ord; P.m_g[pos] = g; }
           ++pos;
         });
@@ -789,6 +851,13 @@ __device__ __forceinline__ void load_pair(const VerifyParams &P, int64_t q0, int
 struct __align__(16) PairTile {  // 20 floats: A,B,C of the query, A',B',C' of the keyframe, max |coord|, pad
   float4 v[5];
 };
+__device__ __forceinline__ float resid2_f32(const float *Rf, const float *tf, float px, float py, float pz, float bx,
+                                            float by, float bz) {
+  const float rx = fmaf(Rf[0], px, fmaf(Rf[1], py, fmaf(Rf[2], pz, tf[0]))) - bx;
+  const float ry = fmaf(Rf[3], px, fmaf(Rf[4], py, fmaf(Rf[5], pz, tf[1]))) - by;
+  const float rz = fmaf(Rf[6], px, fmaf(Rf[7], py, fmaf(Rf[8], pz, tf[2]))) - bz;
+  return fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+}
 __device__ __forceinline__ bool vertex_inlier_fast(const float *Rf, const float *tf, const double *R, const double *t,
                                                    float px, float py, float pz, float bx, float by, float bz,
                                                    float margin) {
@@ -830,6 +899,7 @@ __global__ void __launch_bounds__(kVerifyThreads) k_verify(VerifyParams P) {
   for (int i = 0; i < 9; ++i) Rf[i] = (tid < H) ? (float)R[i] : 0.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) { tf[i] = (tid < H) ? (float)t[i] : 0.f; tmax = fmaxf(tmax, fabsf(tf[i])); }
+  const float mt = fminf(fmaf(4.0e-5f, tmax, 1.0e-4f), 8.0f);
   int vote = 0;
   for (int jb = 0; jb < M; jb += kVerifyThreads) {
     const int nt = min(kVerifyThreads, M - jb);
@@ -843,7 +913,7 @@ __global__ void __launch_bounds__(kVerifyThreads) k_verify(VerifyParams P) {
       PairTile pt;
       pt.v[0] = make_float4(a[0], a[1], a[2], a[3]); pt.v[1] = make_float4(a[4], a[5], a[6], a[7]);
       pt.v[2] = make_float4(a[8], b[0], b[1], b[2]); pt.v[3] = make_float4(b[3], b[4], b[5], b[6]);
-      pt.v[4] = make_float4(b[7], b[8], mx, 0.f);
+      pt.v[4] = make_float4(b[7], b[8], fminf(fmaf(4.0e-5f, mx, 1.0e-4f), 8.0f), 0.f);  // .z = margin of the pair
       s_pair[tid] = pt;
     }
     __syncthreads();
@@ -851,8 +921,17 @@ __global__ void __launch_bounds__(kVerifyThreads) k_verify(VerifyParams P) {
       for (int jj = 0; jj < nt; ++jj) {
         const float4 v0 = s_pair[jj].v[0], v1 = s_pair[jj].v[1], v2 = s_pair[jj].v[2], v3 = s_pair[jj].v[3],
                      v4 = s_pair[jj].v[4];
-        // margin(X) = 16 * 40 * eps32 * X (+ slack), X = max |coordinate| of the pair and |t|
-        const float margin = fminf(fmaf(4.0e-5f, fmaxf(v4.z, tmax), 1.0e-4f), 8.0f);
+        // margin(X) = 16 * 40 * eps32 * X (+ slack), X = max |coordinate| of the pair and |t|;
+        // v4.z already holds the pair's margin, mt this hypothesis' own
+        const float margin = fmaxf(v4.z, mt);
+        // straight-line FP32 residuals of the three vertices (independent FMA chains)
+        const float dA = resid2_f32(Rf, tf, v0.x, v0.y, v0.z, v2.y, v2.z, v2.w);
+        const float dB = resid2_f32(Rf, tf, v0.w, v1.x, v1.y, v3.x, v3.y, v3.z);
+        const float dC = resid2_f32(Rf, tf, v1.z, v1.w, v2.x, v3.w, v4.x, v4.y);
+        const float lo = 9.0f - margin, hi = 9.0f + margin;
+        if (dA < lo && dB < lo && dC < lo) { ++vote; continue; }  // clearly an inlier
+        if (dA > hi || dB > hi || dC > hi) continue;              // clearly not
+        // some vertex is inside the band (or not comparable): decide it exactly
         const bool ok = vertex_inlier_fast(Rf, tf, R, t, v0.x, v0.y, v0.z, v2.y, v2.z, v2.w, margin) &&
                         vertex_inlier_fast(Rf, tf, R, t, v0.w, v1.x, v1.y, v3.x, v3.y, v3.z, margin) &&
                         vertex_inlier_fast(Rf, tf, R, t, v1.z, v1.w, v2.x, v3.w, v4.x, v4.y, margin);
