@@ -53,6 +53,11 @@ def parse():
     ap.add_argument("--cpu-queries", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=8192, help="keyframes per DB-build batch")
+    ap.add_argument("--workload", default="city", choices=["city", "seq"],
+                    help="city: configs[3] node-level DB (default, the metric's config); "
+                         "seq: configs[1]-shaped labelled-scan sequence, stages 1-4 per query scan")
+    ap.add_argument("--scans", type=int, default=1024, help="seq: map keyframes (scans)")
+    ap.add_argument("--batch", type=int, default=32, help="seq: query scans per call")
     return ap.parse_args()
 
 
@@ -388,9 +393,166 @@ def run_ours(args):
     mgr.close()
 
 
+# ------------------------------------------------------------------------------------------
+def run_seq(args):
+    """configs[1]-shaped workload: a synthetic street sequence of labelled 64-beam scans.  The map is
+    built from scans (stage 1 -> stage 2 -> add); every query is a labelled SCAN of a revisited place
+    (new noise, lateral offset, random yaw) pushed through stages 1-4.  Single GPU."""
+    import torch
+    from sgtd_b200 import capi, synth_seq, synth
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    w = synth_seq.make_street_world(args.scans, synth.BASE_SEED + 1)
+    P = w["poses"]
+    mgr = capi.STDescManager(device=0)
+    nq = min(args.queries, 256) if args.queries == 1024 else args.queries
+    B = args.batch
+
+    def render_batch(poses, seed0):
+        pts, labs, off = [], [], [0]
+        for i, ps in enumerate(poses):
+            p, l = synth_seq.render_at(w, ps, seed0 + i, device=dev)
+            pts.append(p); labs.append(l.to(torch.int32)); off.append(off[-1] + p.shape[0])
+        return torch.cat(pts).contiguous(), torch.cat(labs).contiguous(), np.array(off, np.int64)
+
+    # ---- map pass (not timed) ----
+    t0 = time.time()
+    few = 0
+    for c0 in range(0, args.scans, B):
+        pts, labs, off = render_batch(P[c0:c0 + B], 10_000 + c0)
+        nodes, noff, _ = mgr.extract_instances_ptr(pts.data_ptr(), labs.data_ptr(), off)
+        for s in range(len(off) - 1):
+            nd = nodes[noff[s]:noff[s + 1]]
+            if nd.shape[0] >= 10:
+                b = mgr.build(nd, frame_ids=np.array([c0 + s], np.uint32))
+            else:            # too few instances for a descriptor: keep the frame id, add nothing
+                few += 1
+                b = mgr.upload(np.zeros(0, capi.DESC_DTYPE), np.zeros(2, np.int64))
+            mgr.add(b); b.free()
+    mgr.finalize()
+    t_map = time.time() - t0
+    # ---- queries: revisited places, new noise, +-1.5 m lateral offset, random yaw ----
+    rng = np.random.default_rng(synth.BASE_SEED + 2)
+    gt = rng.integers(0, args.scans, nq)
+    qposes = P[gt].copy()
+    qposes[:, :2] += rng.uniform(-1.5, 1.5, (nq, 2))
+    qposes[:, 2] = rng.uniform(-np.pi, np.pi, nq)
+    batches = []
+    for c0 in range(0, nq, B):
+        pts, labs, off = render_batch(qposes[c0:c0 + B], 900_000 + c0)
+        batches.append((pts, labs, off, pts.cpu().pin_memory(), labs.cpu().pin_memory()))
+    k = mgr.cfg.candidate_num
+    out_loops = np.zeros(nq, capi.LOOP_DTYPE)
+    out_cands = np.zeros((nq, k), capi.CAND_DTYPE)
+    stage = {}
+
+    def step(host):
+        c0 = 0
+        for (pts, labs, off, hp, hl) in batches:
+            t = [time.perf_counter()]
+            if host:
+                nodes, noff, _, _ = mgr.extract_instances(hp.numpy(), hl.numpy().view(np.uint32), off, want_membership=False)
+            else:
+                nodes, noff, _ = mgr.extract_instances_ptr(pts.data_ptr(), labs.data_ptr(), off)
+            t.append(time.perf_counter())
+            ok = np.diff(noff) >= 10
+            sel = np.concatenate([nodes[noff[s]:noff[s + 1]] for s in range(len(ok)) if ok[s]]) if ok.any() else nodes[:0]
+            soff = np.concatenate([[0], np.cumsum(np.diff(noff)[ok])]).astype(np.int64)
+            qb = mgr.build(sel, soff)
+            t.append(time.perf_counter())
+            res = mgr.search(qb)
+            loops, cands = res.download()
+            t.append(time.perf_counter())
+            idx = c0 + np.nonzero(ok)[0]
+            out_loops[idx] = loops; out_cands[idx] = cands
+            out_loops["frame"][c0 + np.nonzero(~ok)[0]] = -1
+            res.free(); qb.free()
+            c0 += len(ok)
+            for name, a, b_ in (("stage1_ms", 0, 1), ("stage2_ms", 1, 2), ("stage34_ms", 2, 3)):
+                stage[name] = stage.get(name, 0.0) + (t[b_] - t[a]) * 1e3
+
+    def timed(host, steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step(host)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
+    for _ in range(args.warmup):
+        step(False); step(True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    stage.clear()
+    l0 = mgr.kernel_launches
+    ms_dev = timed(False, args.steps)
+    launches = mgr.kernel_launches - l0
+    st_dev = {kk: round(vv / args.steps, 2) for kk, vv in stage.items()}
+    ms_e2e = timed(True, args.steps)
+    clocks = sampler.stop()
+
+    def se3(pose):
+        c_, s_ = np.cos(pose[2]), np.sin(pose[2])
+        T = np.eye(4)
+        T[:2, :2] = [[c_, -s_], [s_, c_]]
+        T[:2, 3] = pose[:2]
+        return T
+    succ, found, terr, rerr = 0, 0, [], []
+    for qi in range(nq):
+        f = out_loops["frame"][qi]
+        if f < 0:
+            continue
+        found += 1
+        c = [c for c in out_cands[qi] if c["frame"] == f and c["score"] == out_loops["score"][qi]][0]
+        Tl = np.eye(4)
+        Tl[:3, :3] = c["R"].reshape(3, 3); Tl[:3, 3] = c["t"]
+        d = np.linalg.inv(se3(P[f]) @ Tl) @ se3(qposes[qi])
+        te = float(np.linalg.norm(d[:3, 3]))
+        re = float(np.degrees(np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1))))
+        if te < 5.0 and re < 10.0:
+            succ += 1; terr.append(te); rerr.append(re)
+    npts = int(sum(b[2][-1] for b in batches))
+    line = {"metric": METRIC, "value": nq * args.steps / (ms_dev * 1e-3), "unit": "queries/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]-shaped: synthetic street sequence, labelled 64-beam scans, stages 1-4 per query",
+                       "map_scans": args.scans, "queries": nq, "points_per_scan": npts // nq, "batch": B,
+                       "db_descriptors": int(mgr.db_size), "map_build_s": round(t_map, 1), "map_scans_with_too_few_nodes": few,
+                       "timing": "wall clock around synchronous C-ABI calls (device work is synchronised inside each call)"},
+            "e2e": {"value": nq * args.steps / (ms_e2e * 1e-3), "unit": "queries/s",
+                    "h2d_bytes_per_step": npts * 20, "d2h_bytes_per_step": int(nq * (16 + k * 136))},
+            "gpu_launches": int(launches), "stage_ms_per_step": st_dev,
+            "recall": {"queries": nq, "found": found, "success_T5m_R10deg": succ,
+                       "rmse_t_m": float(np.sqrt(np.mean(np.square(terr)))) if terr else None,
+                       "rmse_r_deg": float(np.sqrt(np.mean(np.square(rerr)))) if rerr else None},
+            "clocks": clocks}
+    if not args.no_cpu_baseline:
+        from oracle import orc
+        o = orc.Oracle()
+        # the oracle DB is built from the oracle's own stage 1+2 on a bounded prefix of the map
+        nmap = min(args.scans, 64)
+        for f in range(nmap):
+            p_, l_ = synth_seq.render_at(w, P[f], 10_000 + (f // B) * B + f % B, device="cpu")
+            r = orc.extract_instances(p_.numpy(), l_.numpy().astype(np.uint32))
+            o.add(o.build(r["node_xyz"], r["node_label"]) if len(r["node_label"]) >= 10 else np.zeros(0, orc.DESC_DTYPE))
+        pts, labs, off, hp, hl = batches[0]
+        n_cpu = min(8, len(off) - 1)
+        t0 = time.time()
+        for s in range(n_cpu):
+            r = orc.extract_instances(hp.numpy()[off[s]:off[s + 1]], hl.numpy().view(np.uint32)[off[s]:off[s + 1]])
+            if len(r["node_label"]) >= 10:
+                o.search(o.build(r["node_xyz"], r["node_label"]), nthreads=os.cpu_count() or 1, want_votes=False)
+        line["cpu_baseline"] = {"value": n_cpu / (time.time() - t0), "unit": "queries/s", "cores": os.cpu_count() or 1,
+                                "kind": "port", "sample": f"{n_cpu} query scans, stages 1-4, against the first {nmap} map scans"}
+    print(json.dumps(line))
+    mgr.close()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "seq":
+        run_seq(a)
     else:
         run_ours(a)

@@ -359,6 +359,18 @@ class STDescManager:
                                                      _p(nodes), cap, _p(noff), _p(ninst)))
         return nodes[:noff[ns]].copy(), noff, pi, ninst[:ns]
 
+    def extract_instances_ptr(self, points_ptr, labels_ptr, offsets):
+        """Same, for scans already resident on the device (raw pointers); no membership output."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        ns = offsets.shape[0] - 1
+        cap = 4096 * max(ns, 1)
+        nodes = np.zeros(cap, NODE_DTYPE)
+        noff = np.zeros(ns + 1, np.int64)
+        ninst = np.zeros(max(ns, 1), np.int32)
+        self._chk(lib().sgtd_extract_instances_batch(self._h, _p(points_ptr), _p(labels_ptr), _p(offsets), ns, None,
+                                                     _p(nodes), cap, _p(noff), _p(ninst)))
+        return nodes[:noff[ns]].copy(), noff, ninst[:ns]
+
 
 def graph_write_json(path, nodes, poses12=None):
     nodes = np.ascontiguousarray(nodes, NODE_DTYPE)

@@ -65,7 +65,8 @@ struct S1Buffers {
   int *cls_idx;      // original (scan-local) point index of each class point, ascending
   double *polar;     // 3 per point
   int *slot;         // voxel slot per point
-  int *events;       // compacted local ranks
+  int4 *events;      // seed events in point order: (local rank, voxel slot, packed voxel coords, -)
+  int *nbr;          // 27 neighbour slots per event
   int *pt_label;     // labels of points of invisible voxels
   int *final_label;  // final label per point
   int *parent, *count, *first;  // per label value
@@ -247,64 +248,96 @@ __global__ void __launch_bounds__(kS1Threads) k_dcvc_prepare(S1Buffers B, double
     }
     int total;
     const int p = block_excl_scan(ev, s_warp, total);
-    if (ev) B.events[t.idx_off + base + p] = r;
+    if (ev) {
+      const int pos = B.slot[t.idx_off + r];
+      const int which = (__ldcg(&t_min1[pos]) == r ? 1 : 0) | (__ldcg(&t_min2[pos]) == r ? 2 : 0);
+      B.events[t.idx_off + base + p] = make_int4(r, pos, __ldcg(&t_coord[pos]), which);
+    }
     base += total;
   }
   if (tid == 0) B.ts[blockIdx.x].nevents = base;
+  __syncthreads();
+  // 4. neighbour voxel slots of every event, searchKNN order (:365-385): z (pitch) outer, y (polar),
+  //    x (azimuth) inner; -1 = skipped by the guards or no such voxel.  Parallel here, so that the
+  //    sequential replay only has to read 27 consecutive ints per event.
+  const int nev = base;
+  int *nbr = B.nbr + 27 * t.idx_off;
+  for (int w = tid; w < nev * 27; w += kS1Threads) {
+    const int e = w / 27, k = w - e * 27;
+    const int coord = B.events[t.idx_off + e].z;
+    const int az = coord & 1023, po = (coord >> 10) & 2047, pi = coord >> 21;
+    const int z = pi - 1 + k / 9, y = po - 1 + (k / 3) % 3, x = az - 1 + k % 3;
+    int nb = -1;
+    if (!(z < 0 || z > height) && !(y < 0 || y > polarNum)) {
+      int ax = x;
+      if (ax < 0) ax = width - 1;
+      if (ax > 300) ax = 300;
+      nb = table_lookup(t_key, mask, (ax * (polarNum + 1) + y) + z * (polarNum + 1) * (width + 1));
+    }
+    nbr[w] = nb;
+  }
 }
 
-__device__ __forceinline__ int uf_find(int *parent, int x) {
-  int r = x;
-  while (true) { const int p = __ldcg(parent + r); if (p == r) break; r = p; }
-  while (x != r) { const int p = __ldcg(parent + x); parent[x] = r; x = p; }  // path compression
-  return r;
-}
 __device__ __forceinline__ int uf_find_ro(const int *parent, int x) {
   while (true) { const int p = __ldcg(parent + x); if (p == x) return x; x = p; }
 }
 
+// Union-find over label values: the first kUfSmem labels live in shared memory (every task of the
+// test and bench workloads fits), the rest in the task's global array.
+constexpr int kUfSmem = 8192;
+struct UnionFind {
+  int *sm, *gl;
+  __device__ __forceinline__ int get(int x) const { return x < kUfSmem ? sm[x] : __ldcg(gl + x); }
+  __device__ __forceinline__ void set(int x, int v) { if (x < kUfSmem) sm[x] = v; else gl[x] = v; }
+  __device__ __forceinline__ int find(int x) {
+    int r = x;
+    while (true) { const int p = get(r); if (p == r) break; r = p; }
+    while (x != r) { const int p = get(x); set(x, r); x = p; }  // path compression
+    return r;
+  }
+};
+
 // ---- K4: sequential replay of the seed events, one warp per task (DCVC, :272-355) ---------
+// Per event the warp reads one prefetched record + 27 precomputed neighbour slots, gathers the 27
+// voxel states in parallel, and lane 0 applies the reference's walk.
 __global__ void __launch_bounds__(32) k_dcvc_replay(S1Buffers B) {
   __shared__ int s_nb[27], s_st[27], s_lb[27];
+  __shared__ int s_parent[kUfSmem];
   const Task t = B.tasks[blockIdx.x];
   if (t.policy != P_DCVC) return;
   const int lane = threadIdx.x;
   const TaskState ts = B.ts[blockIdx.x];
-  const int width = ts.width, height = ts.height, polarNum = ts.polarNum;
-  const int *t_key = B.t_key + t.tab_off, *t_min1 = B.t_min1 + t.tab_off, *t_min2 = B.t_min2 + t.tab_off;
-  const int *t_coord = B.t_coord + t.tab_off;
+  const int height = ts.height;
+  const int *t_min1 = B.t_min1 + t.tab_off, *t_min2 = B.t_min2 + t.tab_off;
   int *t_kind = B.t_kind + t.tab_off, *t_label = B.t_label + t.tab_off;
-  int *parent = B.parent + t.lab_off;
+  UnionFind uf{s_parent, B.parent + t.lab_off};
   int *pt_label = B.pt_label + t.idx_off;
-  const int *events = B.events + t.idx_off, *slot = B.slot + t.idx_off;
-  const int mask = t.tab_size - 1;
+  const int4 *events = B.events + t.idx_off;
+  const int *nbr = B.nbr + 27 * t.idx_off;
   int labelCount = 0;
-  for (int e = 0; e < ts.nevents; ++e) {
-    const int r = events[e];
-    const int v = slot[r];
-    const int coord = __ldcg(t_coord + v);
-    const int az = coord & 1023, po = (coord >> 10) & 2047, pi = coord >> 21;
-    const bool vis = pi <= height;
-    if (vis) {  // is the point still unlabelled?
-      const int kd = __ldcg(t_kind + v);
+  const int nev = ts.nevents;
+  // software pipeline: record and neighbour row of event e+1 are in flight while e is processed
+  int4 ev_next = nev > 0 ? events[0] : make_int4(0, 0, 0, 0);
+  int nb_next = (nev > 0 && lane < 27) ? nbr[lane] : -1;
+  for (int e = 0; e < nev; ++e) {
+    const int4 ev = ev_next;
+    const int nb_cur = nb_next;
+    if (e + 1 < nev) {
+      ev_next = events[e + 1];
+      if (lane < 27) nb_next = nbr[(e + 1) * 27 + lane];
+    }
+    const int r = ev.x, v = ev.y;
+    const bool vis = (ev.z >> 21) <= height;
+    // one round trip per event: the 27 neighbour states (a visible voxel is its own neighbour 13)
+    const int st_cur = (lane < 27 && nb_cur >= 0) ? __ldcg(t_kind + nb_cur) : K_NONE;
+    const int lb_cur = (lane < 27 && nb_cur >= 0) ? __ldcg(t_label + nb_cur) : -1;
+    if (vis) {  // is the point still unlabelled?  (ev.w: bit0 = lowest point of its voxel, bit1 = second lowest)
+      const int kd = __shfl_sync(0xffffffffu, st_cur, 13);
       if (kd == K_ALL) continue;
-      if (kd == K_NONE && __ldcg(t_min1 + v) != r) continue;
-      if (kd == K_HEAD && __ldcg(t_min2 + v) != r) continue;
+      if (kd == K_NONE && !(ev.w & 1)) continue;
+      if (kd == K_HEAD && !(ev.w & 2)) continue;
     }
-    // searchKNN (:365-385): z (pitch) outer, y (polar), x (azimuth) inner
-    if (lane < 27) {
-      const int z = pi - 1 + lane / 9, y = po - 1 + (lane / 3) % 3, x = az - 1 + lane % 3;
-      int nb = -1;
-      if (!(z < 0 || z > height) && !(y < 0 || y > polarNum)) {
-        int ax = x;
-        if (ax < 0) ax = width - 1;
-        if (ax > 300) ax = 300;
-        nb = table_lookup(t_key, mask, (ax * (polarNum + 1) + y) + z * (polarNum + 1) * (width + 1));
-      }
-      s_nb[lane] = nb;
-      s_st[lane] = nb >= 0 ? __ldcg(t_kind + nb) : K_NONE;
-      s_lb[lane] = nb >= 0 ? __ldcg(t_label + nb) : -1;
-    }
+    if (lane < 27) { s_nb[lane] = nb_cur; s_st[lane] = st_cur; s_lb[lane] = lb_cur; }
     __syncwarp();
     if (lane == 0) {
       int cur = -1;
@@ -316,16 +349,16 @@ __global__ void __launch_bounds__(32) k_dcvc_replay(S1Buffers B) {
         if (st == K_NONE) {
           if (cur != -1) { t_kind[nb] = K_ALL; t_label[nb] = cur; if (nb == v) self_all = true; }
         } else {
-          const int lab = uf_find(parent, s_lb[k]);
+          const int lab = uf.find(s_lb[k]);
           if (cur == -1) cur = lab;
-          else if (cur != lab) { parent[cur] = lab; cur = lab; }  // relabel sweep cur -> neigh (:323-327)
+          else if (cur != lab) { uf.set(cur, lab); cur = lab; }  // relabel sweep cur -> neigh (:323-327)
           if (st == K_HEAD) t_kind[nb] = K_ALL;
           if (nb == v) self_all = true;
         }
       }
       if (cur == -1) {  // new label for the seed and every neighbour (:340-346)
         const int L = ++labelCount;
-        parent[L] = L;
+        uf.set(L, L);
         for (int k = 0; k < 27; ++k) { const int nb = s_nb[k]; if (nb >= 0) { t_kind[nb] = K_ALL; t_label[nb] = L; } }
         if (!vis) pt_label[r] = L;
       } else if (vis) {
@@ -336,6 +369,10 @@ __global__ void __launch_bounds__(32) k_dcvc_replay(S1Buffers B) {
     }
     __syncwarp();
   }
+  // publish the shared-memory part of the union-find for k_s1_finish
+  __syncwarp();
+  labelCount = __shfl_sync(0xffffffffu, labelCount, 0);  // only lane 0 counted
+  for (int i = 1 + lane; i <= labelCount && i < kUfSmem; i += 32) uf.gl[i] = s_parent[i];
   if (lane == 0) B.ts[blockIdx.x].labelCount = labelCount;
 }
 
@@ -417,25 +454,39 @@ __global__ void __launch_bounds__(kS1Threads) k_s1_assign(S1Buffers B, const int
 }
 
 // ---- K7: centroid = sequential float32 sum in ascending point order (get_json.cpp:266-274) ----
-__global__ void k_s1_centroid(S1Buffers B, const InstRec *inst, int ninst, sgtd_node *nodes) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per instance: 32 class points are fetched per trip (coalesced), the lanes that belong to
+// the instance are then added in lane order, so the rounding sequence is the reference's.
+__global__ void __launch_bounds__(128) k_s1_centroid(S1Buffers B, const InstRec *inst, int ninst, sgtd_node *nodes) {
+  const int i = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= ninst) return;
   const InstRec ir = inst[i];
   if (ir.node_slot < 0) return;
   const Task t = B.tasks[ir.task];
   float cx = 0.f, cy = 0.f, cz = 0.f;
   int n = 0;
-  for (int r = 0; r < t.npts; ++r) {
-    if (B.final_label[t.idx_off + r] != ir.label) continue;
-    const float4 p = B.pts[t.pt0 + B.cls_idx[t.idx_off + r]];
-    cx = __fadd_rn(cx, p.x); cy = __fadd_rn(cy, p.y); cz = __fadd_rn(cz, p.z);
-    ++n;
+  for (int r0 = 0; r0 < t.npts; r0 += 32) {
+    const int r = r0 + lane;
+    const bool mine = r < t.npts && B.final_label[t.idx_off + r] == ir.label;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mine) p = B.pts[t.pt0 + B.cls_idx[t.idx_off + r]];
+    unsigned m = __ballot_sync(0xffffffffu, mine);
+    n += __popc(m);
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      cx = __fadd_rn(cx, __shfl_sync(0xffffffffu, p.x, l));
+      cy = __fadd_rn(cy, __shfl_sync(0xffffffffu, p.y, l));
+      cz = __fadd_rn(cz, __shfl_sync(0xffffffffu, p.z, l));
+    }
   }
-  const float cnt = (float)n;
-  sgtd_node nd;
-  nd.x = __fdiv_rn(cx, cnt); nd.y = __fdiv_rn(cy, cnt); nd.z = __fdiv_rn(cz, cnt);
-  nd.label = ir.node_label;
-  nodes[ir.node_slot] = nd;
+  if (lane == 0) {
+    const float cnt = (float)n;
+    sgtd_node nd;
+    nd.x = __fdiv_rn(cx, cnt); nd.y = __fdiv_rn(cy, cnt); nd.z = __fdiv_rn(cz, cnt);
+    nd.label = ir.node_label;
+    nodes[ir.node_slot] = nd;
+  }
 }
 
 __global__ void k_fill_i32(int *p, int64_t n, int v) {
@@ -449,6 +500,23 @@ static int node_map(int c) {  // R/src/get_json.cpp:10-12 ; -1 = key absent (lab
     case 0: case 1: case 2: case 3: case 4: case 5: case 6: case 7: case 8: case 19: return 0;
     default: return -1;
   }
+}
+
+struct S1Pool {
+  DevBuf<int64_t> d_off; DevBuf<uint32_t> d_cnt; DevBuf<Task> d_tasks; DevBuf<TaskState> d_ts;
+  DevBuf<int> d_pp, d_tab, d_lab, d_pool, d_map; DevBuf<double> d_polar, d_bounds; DevBuf<unsigned long long> d_cur;
+  DevBuf<InstRec> d_inst; DevBuf<sgtd_node> d_nodes;
+  DevBuf<float4> in_pts; DevBuf<uint32_t> in_lab; DevBuf<int32_t> out_pi;  // staging of host inputs / outputs
+  ~S1Pool() {
+    d_off.release(); d_cnt.release(); d_tasks.release(); d_ts.release(); d_pp.release(); d_tab.release(); d_lab.release();
+    d_pool.release(); d_map.release(); d_polar.release(); d_bounds.release(); d_cur.release(); d_inst.release();
+    d_nodes.release(); in_pts.release(); in_lab.release(); out_pi.release();
+  }
+};
+static void s1_pool_free(void *p) { delete static_cast<S1Pool *>(p); }
+static S1Pool &s1_pool(sgtd_handle *h) {
+  if (!h->s1pool) { h->s1pool = new S1Pool(); h->s1pool_free = s1_pool_free; }
+  return *static_cast<S1Pool *>(h->s1pool);
 }
 
 #define S1_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rc = sgtd_fail(h, SGTD_E_CUDA, #expr, __FILE__, __LINE__, _e); goto done; } } while (0)
@@ -466,9 +534,13 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
   nodes_out.clear();
   if (nscans == 0) return SGTD_OK;
   // device-side temporaries (freed at the end; stage 1 is not on the per-query path)
-  DevBuf<int64_t> d_off; DevBuf<uint32_t> d_cnt; DevBuf<Task> d_tasks; DevBuf<TaskState> d_ts;
-  DevBuf<int> d_pp, d_tab, d_lab, d_pool, d_map; DevBuf<double> d_polar, d_bounds; DevBuf<unsigned long long> d_cur;
-  DevBuf<InstRec> d_inst; DevBuf<sgtd_node> d_nodes;
+  // device-side temporaries live in a per-handle pool: steady-state calls do no cudaMalloc/cudaFree
+  S1Pool &sp = s1_pool(h);
+  DevBuf<int64_t> &d_off = sp.d_off; DevBuf<uint32_t> &d_cnt = sp.d_cnt; DevBuf<Task> &d_tasks = sp.d_tasks;
+  DevBuf<TaskState> &d_ts = sp.d_ts;
+  DevBuf<int> &d_pp = sp.d_pp, &d_tab = sp.d_tab, &d_lab = sp.d_lab, &d_pool = sp.d_pool, &d_map = sp.d_map;
+  DevBuf<double> &d_polar = sp.d_polar, &d_bounds = sp.d_bounds; DevBuf<unsigned long long> &d_cur = sp.d_cur;
+  DevBuf<InstRec> &d_inst = sp.d_inst; DevBuf<sgtd_node> &d_nodes = sp.d_nodes;
   std::vector<uint32_t> hc((size_t)nscans * kMaxClass * 2 + 1);
   std::vector<Task> tasks;
   std::vector<TaskState> ts;
@@ -515,7 +587,7 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     S1_CUDA(d_tasks.reserve(nt, st, false)); S1_CUDA(d_ts.reserve(nt, st, false));
     S1_CUDA(cudaMemcpyAsync(d_tasks.p, tasks.data(), nt * sizeof(Task), cudaMemcpyHostToDevice, st));
     S1_CUDA(cudaMemsetAsync(d_ts.p, 0, nt * sizeof(TaskState), st));
-    S1_CUDA(d_pp.reserve((size_t)std::max<int64_t>(n_idx, 1) * 5, st, false));   // cls_idx, slot, events, pt_label, final
+    S1_CUDA(d_pp.reserve((size_t)std::max<int64_t>(n_idx, 1) * (4 + 4 + 27), st, false));  // cls_idx, slot, pt_label, final | events (int4) | nbr
     S1_CUDA(d_polar.reserve((size_t)std::max<int64_t>(n_idx, 1) * 3, st, false));
     S1_CUDA(d_tab.reserve((size_t)std::max<int64_t>(n_tab, 1) * 6, st, false));  // key,min1,min2,coord,kind,label
     S1_CUDA(d_lab.reserve((size_t)std::max<int64_t>(n_lab, 1) * 3, st, false));  // parent,count,first
@@ -524,8 +596,9 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     S1_CUDA(d_cur.reserve(1, st, false));
     S1_CUDA(d_map.reserve((size_t)std::max<int64_t>(n_lab, 1), st, false));
     B.pts = d_pts; B.labels = d_labels; B.tasks = d_tasks.p; B.ts = d_ts.p;
-    B.cls_idx = d_pp.p; B.slot = d_pp.p + n_idx; B.events = d_pp.p + 2 * n_idx; B.pt_label = d_pp.p + 3 * n_idx;
-    B.final_label = d_pp.p + 4 * n_idx;
+    B.cls_idx = d_pp.p; B.slot = d_pp.p + n_idx; B.pt_label = d_pp.p + 2 * n_idx; B.final_label = d_pp.p + 3 * n_idx;
+    B.events = reinterpret_cast<int4 *>(d_pp.p + 4 * n_idx);  // 4*n_idx ints = 16-byte aligned
+    B.nbr = d_pp.p + 8 * n_idx;
     B.polar = d_polar.p;
     B.t_key = d_tab.p; B.t_min1 = d_tab.p + n_tab; B.t_min2 = d_tab.p + 2 * n_tab; B.t_coord = d_tab.p + 3 * n_tab;
     B.t_kind = d_tab.p + 4 * n_tab; B.t_label = d_tab.p + 5 * n_tab;
@@ -604,7 +677,7 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
       S1_CUDA(d_nodes.reserve((size_t)std::max<int64_t>(node_cursor, 1), st, false));
       k_s1_scatter_map<<<(ni + 255) / 256, 256, 0, st>>>(B, d_inst.p, ni, d_map.p);
       if (d_point_instance) k_s1_assign<<<nt, kS1Threads, 0, st>>>(B, d_map.p, d_point_instance);
-      k_s1_centroid<<<(ni + 63) / 64, 64, 0, st>>>(B, d_inst.p, ni, d_nodes.p);
+      k_s1_centroid<<<(ni + 3) / 4, 128, 0, st>>>(B, d_inst.p, ni, d_nodes.p);
       h->launches += 3;
       S1_CUDA(cudaGetLastError());
       if (node_cursor) S1_CUDA(cudaMemcpyAsync(nodes_out.data(), d_nodes.p, (size_t)node_cursor * sizeof(sgtd_node), cudaMemcpyDeviceToHost, st));
@@ -614,8 +687,6 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
   (void)total_pts;
 done:
   cudaStreamSynchronize(st);
-  d_off.release(); d_cnt.release(); d_tasks.release(); d_ts.release(); d_pp.release(); d_tab.release(); d_lab.release();
-  d_pool.release(); d_map.release(); d_polar.release(); d_bounds.release(); d_cur.release(); d_inst.release(); d_nodes.release();
   return rc;
 }
 
@@ -641,7 +712,8 @@ extern "C" int sgtd_extract_instances_batch(sgtd_handle *h, const float *points,
   cudaStream_t st = h->stream;
   std::vector<int64_t> off(scan_offsets, scan_offsets + nscans + 1);
   const int64_t total = nscans ? off[nscans] - off[0] : 0;
-  DevBuf<float4> dp; DevBuf<uint32_t> dl; DevBuf<int32_t> dpi;
+  S1Pool &spool = s1_pool(h);
+  DevBuf<float4> &dp = spool.in_pts; DevBuf<uint32_t> &dl = spool.in_lab; DevBuf<int32_t> &dpi = spool.out_pi;
   const float4 *d_pts = reinterpret_cast<const float4 *>(points) + (nscans ? off[0] : 0);
   const uint32_t *d_lab = labels + (nscans ? off[0] : 0);
   int rc = SGTD_OK;
@@ -681,7 +753,6 @@ extern "C" int sgtd_extract_instances_batch(sgtd_handle *h, const float *points,
       }
     }
   }
-  dp.release(); dl.release(); dpi.release();
   if (prev >= 0 && prev != h->device) cudaSetDevice(prev);
   return rc;
 }

@@ -164,6 +164,8 @@ struct sgtd_handle {
   // objects handed to the caller and not yet freed; sgtd_destroy orphans them (h = nullptr)
   std::unordered_set<sgtd_search_result *> live_results;
   std::unordered_set<sgtd_desc_batch *> live_batches;
+  void *s1pool = nullptr;                 // stage-1 temporaries (instances.cu)
+  void (*s1pool_free)(void *) = nullptr;
   int64_t frame_lo() const { return frames_per_rank ? (int64_t)rank * frames_per_rank : 0; }
   int64_t frames_local() const { return (int64_t)frame_off.size() - 1; }
 };
