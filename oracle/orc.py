@@ -115,7 +115,8 @@ class Oracle:
         xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
         label = np.ascontiguousarray(label, dtype=np.uint32)
         K = xyz.shape[0]
-        cap = max(36 * K, 1)
+        near = self.cfg["descriptor_near_num"]
+        cap = max((near - 1) * (near - 2) // 2 * K, 1)  # all (m, n) pairs of every anchor
         out = np.zeros(cap, dtype=DESC_DTYPE)
         n = lib().orc_build(self._h, _p(xyz), _p(label), K, _p(out), cap)
         if n < 0:

@@ -140,6 +140,65 @@ def test_vote_formulations_agree(world, built, monkeypatch):
             assert cur[2] == ref[2]
 
 
+@pytest.mark.parametrize("over", [
+    dict(std_side_resolution=0.5, descriptor_near_num=8, candidate_num=10, rough_dis_threshold=0.05),
+    dict(std_side_resolution=0.2, descriptor_min_len=2.0, descriptor_max_len=30.0, candidate_num=64, icp_threshold=30.0),
+    dict(descriptor_near_num=16, candidate_num=5, rough_dis_threshold=0.01),
+])
+def test_parity_with_other_configs(oracle_lib, over):
+    """ConfigSetting values other than the shipped YAML: side scaling (key ranges grow), kNN width,
+    candidate count, thresholds."""
+    cfg = synth.make_config(1, 150, 3)
+    xyz, lab, off = cfg["db"]
+    qx, ql, qo = cfg["queries"]
+    nf = off.shape[0] - 1
+    mgr = capi.STDescManager(device=0, **over)
+    o = oracle_lib.Oracle(**over)
+    b = mgr.build(capi.make_nodes(xyz, lab), off, frame_ids=np.arange(nf, dtype=np.uint32))
+    gd, goff = b.download()
+    for f in range(nf):
+        od = o.build(xyz[off[f]:off[f + 1]], lab[off[f]:off[f + 1]])
+        if f % 25 == 0:
+            check_descs(gd[goff[f]:goff[f + 1]], od)
+        o.add(od)
+    mgr.add(b)
+    qb = mgr.build(capi.make_nodes(qx, ql), qo)
+    res = mgr.search(qb)
+    loops, cands = res.download()
+    k = over.get("candidate_num", 50)
+    assert cands.shape[1] == k
+    for q in range(qo.shape[0] - 1):
+        r = o.search(o.build(qx[qo[q]:qo[q + 1]], ql[qo[q]:qo[q + 1]]))
+        assert (res.votes(q, nf) == r["votes"]).all()
+        n = r["n"]
+        assert loops["ncand"][q] == n
+        for key in ("frame", "votes", "score", "best_hyp", "ninlier"):
+            assert (cands[key][q, :n] == r["cands"][key]).all(), key
+        for c in range(n):
+            m_q, m_cell, m_g = res.matches(q, c, int(cands["nmatch"][q, c]))
+            s = slice(r["cands"]["match_off"][c], r["cands"]["match_off"][c] + r["cands"]["nmatch"][c])
+            assert (m_q == r["m_q"][s]).all() and (m_cell == r["m_cell"][s]).all() and (m_g == r["m_g"][s]).all()
+        assert loops["frame"][q] == r["best"][0] and loops["score"][q] == r["best"][1]
+
+
+def test_dense_scan_stress(oracle_lib):
+    """configs[4]-shaped: scans with > 500 instance nodes (kNN tiles, triangle enumeration, dedup)."""
+    rng = np.random.default_rng(17)
+    mgr = capi.STDescManager(device=0)
+    o = oracle_lib.Oracle()
+    Ks = [520, 777, 1500, 10, 64]
+    xyz = [np.column_stack([rng.uniform(-80, 80, (K, 2)), rng.uniform(-2, 6, K)]).astype(np.float32) for K in Ks]
+    # a regular lattice block produces many identical side triples -> exercises first-come-wins dedup
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), [0.0]), -1).reshape(-1, 3).astype(np.float32) * 2.5
+    xyz.append(g); Ks.append(g.shape[0])
+    labs = [rng.integers(3, 12, K).astype(np.uint32) for K in Ks]
+    off = np.concatenate([[0], np.cumsum(Ks)]).astype(np.int64)
+    b = mgr.build(capi.make_nodes(np.concatenate(xyz), np.concatenate(labs)), off)
+    gd, goff = b.download()
+    for s in range(len(Ks)):
+        check_descs(gd[goff[s]:goff[s + 1]], o.build(xyz[s], labs[s]))
+
+
 def test_single_scan_facade_flow(world, oracle_lib):
     """Build/Add one keyframe at a time, as semantic_graph_localization.cpp:419-495 does."""
     xyz, lab, off = world["db"]
