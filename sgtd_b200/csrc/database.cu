@@ -12,7 +12,7 @@
 //                 SoA v_s0/v_s1/v_s2 (f64) + v_frame (u32)  = 28 B per entry,
 //                 coalesced for the bucket scans of the vote kernel.
 //   key table     open addressing, 16 B headers {key, off, cnt}, load <= 0.5.
-//   frame view    per keyframe the (key, g) pairs sorted by key (stable), used to
+//   frame view    per keyframe the (key, g, sides) triples sorted by key (stable), used to
 //                 materialise the match list of a selected candidate keyframe.
 // The two sorts are cub::DeviceRadixSort (library plumbing, database build is
 // not on the query path); every other kernel is hand written.
@@ -56,6 +56,13 @@ __global__ void k_insert_buckets(const uint64_t *ukeys, const uint32_t *offs, co
     if (old == SGTD_EMPTY_KEY) { table[pos].off = offs[i]; table[pos].cnt = cnts[i]; return; }
     pos = (pos + 1) & mask;
   }
+}
+
+__global__ void k_gather_sides(const DescRec *rec, const uint32_t *perm, int64_t n, double *out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const DescRec r = rec[perm[i]];
+  out[3 * i] = r.s[0]; out[3 * i + 1] = r.s[1]; out[3 * i + 2] = r.s[2];
 }
 
 __global__ void k_gather_u64(const uint64_t *src, const uint32_t *perm, int64_t n, uint64_t *dst) {
@@ -151,6 +158,10 @@ int finalize_db(sgtd_handle *h) {
     h->f_key.n = h->f_g.n = (size_t)N;
     SGTD_CUDA(h, cudaMemcpyAsync(h->f_g.p, i0, N * 4, cudaMemcpyDeviceToDevice, st));
     k_gather_u64<<<GB, TB, 0, st>>>(k0, i0, N, h->f_key.p);  // k0 still holds keys in g order
+    SGTD_CUDA(h, h->f_side.reserve((size_t)N * 3, st, false));
+    h->f_side.n = (size_t)N * 3;
+    k_gather_sides<<<GB, TB, 0, st>>>(h->rec.p, i0, N, h->f_side.p);
+    SGTD_LAUNCHED(h);
     SGTD_LAUNCHED(h);
     SGTD_CUDA(h, cudaGetLastError());
   }

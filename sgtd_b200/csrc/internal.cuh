@@ -156,6 +156,7 @@ struct sgtd_handle {
   // per-keyframe key-sorted view (for match-list materialisation)
   sgtd::DevBuf<uint64_t> f_key;
   sgtd::DevBuf<uint32_t> f_g;
+  sgtd::DevBuf<double> f_side;  // side lengths in frame-view order, 3 per entry
   // scratch + recycled objects: steady-state build/search calls do no cudaMalloc/cudaFree
   sgtd::DevBuf<unsigned char> scratch;
   sgtd::DevBuf<unsigned char> stage_in;

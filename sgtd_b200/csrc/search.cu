@@ -485,6 +485,7 @@ struct CollectParams {
   int k;
   const DescRec *q; const QAux *aux; const int64_t *q_off;
   const DescRec *db; const int64_t *frame_off; const uint64_t *f_key; const uint32_t *f_g;
+  const double *f_side;  // side lengths in frame-view (key-sorted) order, 3 per entry
   int64_t frame_lo;
   uint32_t *m_q, *m_g; uint8_t *m_cell;
 };
@@ -518,7 +519,9 @@ struct KeyFinder {
 // (probe ordinal, in-frame position) order
 template <typename Emit>
 __device__ __forceinline__ void desc_vs_frame(const DescRec &r, const QAux &a, const KeyFinder &kf,
-                                              const uint32_t *fg, const DescRec *db, Emit emit) {
+                                              const uint32_t *fg, const double *fside, uint32_t cand_frame,
+                                              Emit emit) {
+  if (r.frame == cand_frame) return;  // (src.frame_id_ - db.frame_id_) > 0 fails for every entry of that keyframe
   // (int)(side + inc) for inc = -1, 0, +1, once per descriptor
   uint32_t cx[3], cy[3], cz[3];
 #pragma unroll
@@ -536,11 +539,10 @@ __device__ __forceinline__ void desc_vs_frame(const DescRec &r, const QAux &a, c
                                   oz == 0 ? cz[0] : (oz == 1 ? cz[1] : cz[2]), r.code);
     int end;
     for (int p = kf.lower_bound(key, end); p < end && kf.keys[p] == key; ++p) {
-      const uint32_t g = fg[p];
-      const DescRec e = db[g];
-      if (e.frame == r.frame) continue;
-      const double d2 = sqn3(__dsub_rn(r.s[0], e.s[0]), __dsub_rn(r.s[1], e.s[1]), __dsub_rn(r.s[2], e.s[2]));
-      if (d2 < a.thr2) emit(ord, g);
+      // sides come from the key-sorted copy (same index as the key): no fg -> db dependent chain
+      const double e0 = fside[3 * p], e1 = fside[3 * p + 1], e2 = fside[3 * p + 2];
+      const double d2 = sqn3(__dsub_rn(r.s[0], e0), __dsub_rn(r.s[1], e1), __dsub_rn(r.s[2], e2));
+      if (d2 < a.thr2) emit(ord, fg[p]);
     }
   }
 }
@@ -597,6 +599,7 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
   }
   __syncthreads();
   const uint32_t *fg = P.f_g + fo;
+  const double *fside = P.f_side + 3 * fo;
   const int64_t q0 = P.q_off[q], q1 = P.q_off[q + 1];
   int64_t base = c.match_off;
   const int64_t limit = c.match_off + c.nmatch;
@@ -607,7 +610,7 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
     DescRec r; QAux a;
     if (i < q1) {
       r = P.q[i]; a = P.aux[i];
-      desc_vs_frame(r, a, kf, fg, P.db, [&](int ord, uint32_t g) {
+      desc_vs_frame(r, a, kf, fg, fside, (uint32_t)c.frame, [&](int ord, uint32_t g) {
 #pragma unroll
         for (int b = 0; b < kCollectBuf; ++b) if (cnt == (uint32_t)b) { bg[b] = g; bo[b] = (uint8_t)ord; }
         ++cnt;
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
         for (int b = 0; b < kCollectBuf; ++b)
           if ((uint32_t)b < cnt && pos + b < limit) { P.m_q[pos + b] = qi; P.m_cell[pos + b] = bo[b]; P.m_g[pos + b] = bg[b]; }
       } else {
-        desc_vs_frame(r, a, kf, fg, P.db, [&](int ord, uint32_t g) {
+        desc_vs_frame(r, a, kf, fg, fside, (uint32_t)c.frame, [&](int ord, uint32_t g) {
           if (pos < limit) { P.m_q[pos] = qi; P.m_cell[pos] = (uint8_t)ord; P.m_g[pos] = g; }
           ++pos;
         });
@@ -1198,7 +1201,7 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
     CollectParams C{};
     C.cands = r->cands.p; C.k = k; C.q = qb->rec.p; C.aux = aux; C.q_off = qb->d_off.p;
     C.db = h->rec.p; C.frame_off = h->d_frame_off.p; C.f_key = h->f_key.p; C.f_g = h->f_g.p;
-    C.frame_lo = h->frame_lo();
+    C.f_side = h->f_side.p; C.frame_lo = h->frame_lo();
     C.m_q = r->m_q.p; C.m_g = r->m_g.p; C.m_cell = r->m_cell.p;
     k_collect<<<(unsigned)nslot, kCollectThreads, 0, st>>>(C);
     SGTD_LAUNCHED(h);
