@@ -216,6 +216,12 @@ int sgtd_result_stats(sgtd_handle *h, const sgtd_search_result *r,
 int sgtd_result_free(sgtd_search_result *r);
 /* Fetch DB descriptors by global index (to build loop_std_pair). */
 int sgtd_db_fetch(sgtd_handle *h, const uint32_t *g, int64_t n, sgtd_desc *out);
+/* Binary snapshot of this rank's keyframe store (the reference rebuilds its database
+ * from the graph JSONs at every start, R/src/semantic_graph_localization.cpp:419-495).
+ * sgtd_db_load needs an empty handle created with the same std_side_resolution and
+ * shard layout; it re-creates the vote index (sgtd_finalize_db). */
+int sgtd_db_save(sgtd_handle *h, const char *path);
+int sgtd_db_load(sgtd_handle *h, const char *path);
 
 /* ---- host-side deterministic top-k merge (same code the GPU merge runs) ---- */
 /* lists: nlists arrays of k (votes, frame) pairs, votes==0 marks an empty

@@ -84,6 +84,8 @@ SYMBOLS = {
     "sgtd_result_stats": (C.c_int, [_VP, _VP, C.POINTER(VoteStats), C.POINTER(Timings)]),
     "sgtd_result_free": (C.c_int, [_VP]),
     "sgtd_db_fetch": (C.c_int, [_VP, _VP, _I64, _VP]),
+    "sgtd_db_save": (C.c_int, [_VP, C.c_char_p]),
+    "sgtd_db_load": (C.c_int, [_VP, C.c_char_p]),
     "sgtd_merge_topk_host": (C.c_int, [_VP, _VP, _I32, _I32, _VP, _VP]),
     "sgtd_nccl_unique_id": (C.c_int, [_VP]),
     "sgtd_shard_init": (C.c_int, [_VP, _I32, _I32, _I64, _VP]),
@@ -339,6 +341,12 @@ class STDescManager:
 
     def synchronize(self):
         self._chk(lib().sgtd_synchronize(self._h))
+
+    def save(self, path):
+        self._chk(lib().sgtd_db_save(self._h, path.encode()))
+
+    def load(self, path):
+        self._chk(lib().sgtd_db_load(self._h, path.encode()))
 
     # -- gen_labels + gen_graphs (stage 1), batched ----------------------------------------------
     def extract_instances(self, points, labels, offsets=None, want_membership=True):

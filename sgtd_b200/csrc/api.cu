@@ -515,6 +515,99 @@ int sgtd_db_fetch(sgtd_handle *h, const uint32_t *g, int64_t n, sgtd_desc *out) 
   return SGTD_OK;
 }
 
+// ---- database snapshot (the reference rebuilds its DB from graph JSONs at every start) ----
+namespace {
+struct SnapHeader {
+  char magic[8];
+  uint32_t abi, current_frame_id;
+  int64_t n_desc, n_frames, frame_lo;
+  int32_t rank, nranks;
+  int64_t frames_per_rank;
+  sgtd_config cfg;
+};
+const char kSnapMagic[8] = {'S', 'G', 'T', 'D', 'D', 'B', '0', '1'};
+}  // namespace
+
+int sgtd_db_save(sgtd_handle *h, const char *path) {
+  if (!h || !path) SGTD_FAIL(h, SGTD_E_INVALID, "bad argument");
+  SetDevice sd(h->device);
+  FILE *f = fopen(path, "wb");
+  if (!f) SGTD_FAIL(h, SGTD_E_IO, "cannot open snapshot for writing");
+  SnapHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  memcpy(hd.magic, kSnapMagic, 8);
+  hd.abi = SGTD_ABI_VERSION; hd.current_frame_id = h->current_frame_id;
+  hd.n_desc = (int64_t)h->rec.n; hd.n_frames = h->frames_local(); hd.frame_lo = h->frame_lo();
+  hd.rank = h->rank; hd.nranks = h->nranks; hd.frames_per_rank = h->frames_per_rank; hd.cfg = h->cfg;
+  bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 &&
+            fwrite(h->frame_off.data(), 8, h->frame_off.size(), f) == h->frame_off.size();
+  const size_t chunk = 1u << 20;  // descriptors per staging copy
+  std::vector<unsigned char> host(chunk * sizeof(DescVert));
+  for (int pass = 0; pass < 2 && ok; ++pass) {
+    const size_t esz = pass ? sizeof(DescVert) : sizeof(DescRec);
+    const unsigned char *src = pass ? (const unsigned char *)h->vert.p : (const unsigned char *)h->rec.p;
+    for (size_t i = 0; i < h->rec.n && ok; i += chunk) {
+      const size_t n = std::min(chunk, h->rec.n - i);
+      cudaError_t e = cudaMemcpyAsync(host.data(), src + i * esz, n * esz, cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { fclose(f); return sgtd_fail(h, SGTD_E_CUDA, "snapshot D2H", __FILE__, __LINE__, e); }
+      ok = fwrite(host.data(), esz, n, f) == n;
+    }
+  }
+  if (fclose(f) != 0) ok = false;
+  if (!ok) SGTD_FAIL(h, SGTD_E_IO, "short write to snapshot");
+  return SGTD_OK;
+}
+
+int sgtd_db_load(sgtd_handle *h, const char *path) {
+  if (!h || !path) SGTD_FAIL(h, SGTD_E_INVALID, "bad argument");
+  if (h->rec.n || h->current_frame_id) SGTD_FAIL(h, SGTD_E_INVALID, "sgtd_db_load needs an empty handle");
+  SetDevice sd(h->device);
+  FILE *f = fopen(path, "rb");
+  if (!f) SGTD_FAIL(h, SGTD_E_IO, "cannot open snapshot");
+  SnapHeader hd;
+  if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, kSnapMagic, 8) != 0 || hd.abi != SGTD_ABI_VERSION ||
+      hd.n_desc < 0 || hd.n_frames < 0) {
+    fclose(f);
+    SGTD_FAIL(h, SGTD_E_IO, "not a sgtd_b200 database snapshot");
+  }
+  // keys depend on the side scaling: refuse a snapshot made with another std_side_resolution
+  if (hd.cfg.std_side_resolution != h->cfg.std_side_resolution || hd.rank != h->rank || hd.nranks != h->nranks ||
+      hd.frames_per_rank != h->frames_per_rank) {
+    fclose(f);
+    SGTD_FAIL(h, SGTD_E_INVALID, "snapshot was made with a different std_side_resolution or shard layout");
+  }
+  std::vector<int64_t> foff((size_t)hd.n_frames + 1);
+  bool ok = fread(foff.data(), 8, foff.size(), f) == foff.size();
+  cudaError_t e = cudaSuccess;
+  if (ok) {
+    e = h->rec.reserve((size_t)std::max<int64_t>(hd.n_desc, 1), h->stream, false);
+    if (e == cudaSuccess) e = h->vert.reserve((size_t)std::max<int64_t>(hd.n_desc, 1), h->stream, false);
+  }
+  const size_t chunk = 1u << 20;
+  std::vector<unsigned char> host(chunk * sizeof(DescVert));
+  for (int pass = 0; pass < 2 && ok && e == cudaSuccess; ++pass) {
+    const size_t esz = pass ? sizeof(DescVert) : sizeof(DescRec);
+    unsigned char *dst = pass ? (unsigned char *)h->vert.p : (unsigned char *)h->rec.p;
+    for (size_t i = 0; i < (size_t)hd.n_desc && ok && e == cudaSuccess; i += chunk) {
+      const size_t n = std::min(chunk, (size_t)hd.n_desc - i);
+      ok = fread(host.data(), esz, n, f) == n;
+      if (ok) {
+        e = cudaMemcpyAsync(dst + i * esz, host.data(), n * esz, cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      }
+    }
+  }
+  fclose(f);
+  if (e != cudaSuccess) return sgtd_fail(h, SGTD_E_CUDA, "snapshot H2D", __FILE__, __LINE__, e);
+  if (!ok) SGTD_FAIL(h, SGTD_E_IO, "truncated snapshot");
+  h->rec.n = h->vert.n = (size_t)hd.n_desc;
+  h->frame_off = foff;
+  h->current_frame_id = hd.current_frame_id;
+  h->dirty = true;
+  return finalize_db(h);
+}
+
 int sgtd_merge_topk_host(const int32_t *votes, const int32_t *frames, int32_t nlists, int32_t k, int32_t *out_votes,
                          int32_t *out_frames) {
   if (!votes || !frames || !out_votes || !out_frames || nlists < 1 || k < 1) return SGTD_E_INVALID;

@@ -199,6 +199,29 @@ def test_dense_scan_stress(oracle_lib):
         check_descs(gd[goff[s]:goff[s + 1]], o.build(xyz[s], labs[s]))
 
 
+def test_db_snapshot_roundtrip(world, built, tmp_path):
+    """sgtd_db_save / sgtd_db_load: a restored database answers queries identically."""
+    mgr, o, *_ = built
+    qx, ql, qo = world["queries"]
+    path = str(tmp_path / "db.sgtd")
+    mgr.save(path)
+    m2 = capi.STDescManager(device=0)
+    m2.load(path)
+    assert m2.current_frame_id_ == mgr.current_frame_id_ and m2.db_size == mgr.db_size
+    qn = capi.make_nodes(qx, ql)
+    l1, c1 = mgr.search(mgr.build(qn, qo)).download()
+    l2, c2 = m2.search(m2.build(qn, qo)).download()
+    assert l1.tobytes() == l2.tobytes() and c1.tobytes() == c2.tobytes()
+    with pytest.raises(capi.SgtdError):
+        m2.load(path)                                   # needs an empty handle
+    m3 = capi.STDescManager(device=0, std_side_resolution=0.5)
+    with pytest.raises(capi.SgtdError):
+        m3.load(path)                                   # keys depend on the side scaling
+    open(path, "r+b").truncate(1000)
+    with pytest.raises(capi.SgtdError):
+        capi.STDescManager(device=0).load(path)
+
+
 def test_single_scan_facade_flow(world, oracle_lib):
     """Build/Add one keyframe at a time, as semantic_graph_localization.cpp:419-495 does."""
     xyz, lab, off = world["db"]
