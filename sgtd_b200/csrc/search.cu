@@ -284,8 +284,10 @@ __global__ void __launch_bounds__(kVoteThreads) k_vote_join(JoinParams P) {
         for (int u = 0; u < kVoteUnroll; ++u) {
           const uint32_t e = e0 + 32 * u + lane;
           const size_t idx = (size_t)o + (e < n ? e : n - 1);
-          a[u] = __ldg(P.s0 + idx); b[u] = __ldg(P.s1 + idx); c[u] = __ldg(P.s2 + idx);
-          f[u] = __ldg(P.fr + idx);
+          // streaming loads (ld.global.cs, evict-first): bucket tiles must not push the vote rows that the
+          // RED.ADDs below keep hitting out of L2
+          a[u] = __ldcs(P.s0 + idx); b[u] = __ldcs(P.s1 + idx); c[u] = __ldcs(P.s2 + idx);
+          f[u] = __ldcs(P.fr + idx);
         }
         for (int p = i; p < i + run; ++p) {
           const double q0 = sh_s[wid][p][0], q1 = sh_s[wid][p][1], q2 = sh_s[wid][p][2], thr2 = sh_s[wid][p][3];
@@ -1126,9 +1128,10 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
       int sbits = 1;
       while ((1ull << sbits) <= h->table_mask) ++sbits;
       // Probes are processed query-group by query-group so that the vote rows being reduced into
-      // (nq/ngroups x F x 4 B) stay L2-resident (~96 MB of the 126 MB L2); more groups = fewer probes
-      // per bucket run, so no more than needed.
-      int ngroups = (int)std::min<int64_t>(16, std::max<int64_t>(1, ((int64_t)nq * Fa * 4 + (96ll << 20) - 1) / (96ll << 20)));
+      // (nq/ngroups x F x 4 B) stay L2-resident while bucket tiles stream past them with evict-first
+      // loads; measured optimum on B200 (126 MB L2): ~50 MB of rows per group.  More groups = fewer
+      // probes per bucket run, so no more than needed.
+      int ngroups = (int)std::min<int64_t>(32, std::max<int64_t>(1, ((int64_t)nq * Fa * 4 + (56ll << 20) - 1) / (56ll << 20)));
       if (getenv("SGTD_JOIN_GROUPS")) ngroups = std::max(1, atoi(getenv("SGTD_JOIN_GROUPS")));
       E2.group_shift = (uint32_t)sbits; E2.group_div = (uint32_t)std::max(1, (nq + ngroups - 1) / ngroups);
       int gbits = 0;
