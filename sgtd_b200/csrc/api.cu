@@ -221,7 +221,7 @@ int sgtd_destroy(sgtd_handle *h) {
   cudaStreamSynchronize(h->stream);
   if (h->nccl) nccl_api().CommDestroy((ncclComm_t)h->nccl);
   h->rec.release(); h->vert.release(); h->d_frame_off.release();
-  h->v_s0.release(); h->v_s1.release(); h->v_s2.release(); h->v_frame.release();
+  h->v_s0.release(); h->v_s1.release(); h->v_s2.release(); h->v_frame.release(); h->v_pack.release();
   h->table.release(); h->f_key.release(); h->f_g.release(); h->f_side.release(); h->scratch.release(); h->stage_in.release();
   if (h->s1pool && h->s1pool_free) h->s1pool_free(h->s1pool);
   for (auto *r : h->result_pool) destroy_result(r);

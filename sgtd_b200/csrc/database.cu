@@ -37,12 +37,13 @@ __global__ void k_make_keys(const DescRec *rec, int64_t n, uint64_t *key, uint32
 }
 
 __global__ void k_gather_index(const DescRec *rec, const uint32_t *perm, int64_t n, uint32_t frame_lo,
-                               double *s0, double *s1, double *s2, uint32_t *fr) {
+                               double *s0, double *s1, double *s2, uint32_t *fr, float4 *pack) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   DescRec r = rec[perm[i]];
   s0[i] = r.s[0]; s1[i] = r.s[1]; s2[i] = r.s[2];
   fr[i] = r.frame - frame_lo;
+  pack[i] = make_float4((float)r.s[0], (float)r.s[1], (float)r.s[2], __uint_as_float(r.frame - frame_lo));
 }
 
 __global__ void k_insert_buckets(const uint64_t *ukeys, const uint32_t *offs, const uint32_t *cnts,
@@ -123,9 +124,10 @@ int finalize_db(sgtd_handle *h) {
   SGTD_LAUNCHED(h);
   SGTD_CUDA(h, h->v_s0.reserve(N, st, false)); SGTD_CUDA(h, h->v_s1.reserve(N, st, false));
   SGTD_CUDA(h, h->v_s2.reserve(N, st, false)); SGTD_CUDA(h, h->v_frame.reserve(N, st, false));
-  h->v_s0.n = h->v_s1.n = h->v_s2.n = h->v_frame.n = (size_t)N;
+  SGTD_CUDA(h, h->v_pack.reserve(N, st, false));
+  h->v_s0.n = h->v_s1.n = h->v_s2.n = h->v_frame.n = h->v_pack.n = (size_t)N;
   k_gather_index<<<GB, TB, 0, st>>>(h->rec.p, i1, N, (uint32_t)h->frame_lo(), h->v_s0.p, h->v_s1.p, h->v_s2.p,
-                                    h->v_frame.p);
+                                    h->v_frame.p, h->v_pack.p);
   SGTD_LAUNCHED(h);
   SGTD_CUDA(h, cudaGetLastError());
   // buckets

@@ -150,6 +150,7 @@ struct sgtd_handle {
   bool dirty = true;
   sgtd::DevBuf<double> v_s0, v_s1, v_s2;
   sgtd::DevBuf<uint32_t> v_frame;  // LOCAL frame index of each entry
+  sgtd::DevBuf<float4> v_pack;     // {float s0, s1, s2, frame bits}: what k_vote_join streams (16 B/entry)
   sgtd::DevBuf<sgtd::Bucket> table;
   uint64_t table_mask = 0;
   int64_t n_buckets = 0;

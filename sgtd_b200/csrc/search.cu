@@ -240,15 +240,44 @@ struct JoinParams {
   const DescRec *q; const QAux *aux;
   const Bucket *table;
   const double *s0, *s1, *s2; const uint32_t *fr;
+  const float4 *pack;  // {float s0, s1, s2, frame bits} per entry, key-major
+  double band;         // relative half-width of the FP32 decision band
   uint32_t frame_lo; int64_t F;
   uint32_t *votes;
   unsigned long long *seg_counter, *counters;
   uint32_t slot_mask;
 };
 
+// FP32 pre-filter of the rough distance test.  DB sides are also kept as float (16-byte packed entry
+// {s0, s1, s2, frame}); the squared distance is first formed in float.  With u = 2^-24, sides <= S'
+// and ||d|| ~ thr at the decision boundary, |d2_f - d2| <= (6.93 u S'/thr + 5 u) thr^2, and
+// S'/thr <= (1 + rough)/rough, so outside the relative band  thr^2 (1 -+ m),
+// m = 2e-6 (1 + 1/rough)  (>= 4x the bound), the float decision equals the reference's FP64 one;
+// inside the band (a ~1e-4 fraction of boundary cases) the entry's FP64 sides are loaded and the
+// exact expression is evaluated.  Halves the bytes per entry and moves the test to the FP32 pipe.
+// Exact (reference) evaluation of the entries a lane found inside the FP32 decision band.
 template <bool kDoVote>
-__global__ void __launch_bounds__(kVoteThreads) k_vote_join(JoinParams P) {
-  __shared__ double sh_s[kVoteThreads / 32][kJoinSeg][4];    // s0, s1, s2, thr2 of each probe of the segment
+__device__ __noinline__ uint32_t join_exact(const JoinParams &P, const double *qs, uint32_t *row, uint32_t o, uint32_t n,
+                                            uint32_t e_first, uint32_t amb) {
+  uint32_t hits = 0;
+  while (amb) {
+    const int u = __ffs(amb) - 1;
+    amb &= amb - 1;
+    const uint32_t e = e_first + 32 * u;
+    const size_t idx = (size_t)o + (e < n ? e : n - 1);
+    const double d2 = sqn3(__dsub_rn(qs[0], P.s0[idx]), __dsub_rn(qs[1], P.s1[idx]), __dsub_rn(qs[2], P.s2[idx]));
+    if (d2 < qs[3]) {
+      if (kDoVote) atomicAdd(row + P.fr[idx], 1u);
+      ++hits;
+    }
+  }
+  return hits;
+}
+
+template <bool kDoVote>
+__global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
+  __shared__ double sh_s[kVoteThreads / 32][kJoinSeg][4];    // s0, s1, s2, thr2 of each probe of the segment (exact path)
+  __shared__ float sh_f[kVoteThreads / 32][kJoinSeg][6];     // float s0, s1, s2, lo, hi of the band
   __shared__ uint32_t sh_q[kVoteThreads / 32][kJoinSeg][2];  // query index, query frame id
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned long long nseg = (P.npairs + kJoinSeg - 1) / kJoinSeg;
@@ -268,6 +297,9 @@ __global__ void __launch_bounds__(kVoteThreads) k_vote_join(JoinParams P) {
       const DescRec r = P.q[d];
       const QAux a = P.aux[d];
       sh_s[wid][lane][0] = r.s[0]; sh_s[wid][lane][1] = r.s[1]; sh_s[wid][lane][2] = r.s[2]; sh_s[wid][lane][3] = a.thr2;
+      sh_f[wid][lane][0] = (float)r.s[0]; sh_f[wid][lane][1] = (float)r.s[1]; sh_f[wid][lane][2] = (float)r.s[2];
+      sh_f[wid][lane][3] = __double2float_rd(a.thr2 * (1.0 - P.band));  // below: certainly a match
+      sh_f[wid][lane][4] = __double2float_ru(a.thr2 * (1.0 + P.band));  // above: certainly not
       sh_q[wid][lane][0] = a.qi; sh_q[wid][lane][1] = r.frame;
     }
     __syncwarp();
@@ -278,29 +310,33 @@ __global__ void __launch_bounds__(kVoteThreads) k_vote_join(JoinParams P) {
       const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.table[cur & P.slot_mask]));
       const uint32_t o = raw.z, n = raw.w;
       for (uint32_t e0 = 0; e0 < n; e0 += 32 * kVoteUnroll) {
-        double a[kVoteUnroll], b[kVoteUnroll], c[kVoteUnroll];
-        uint32_t f[kVoteUnroll];
+        float4 v[kVoteUnroll];
 #pragma unroll
         for (int u = 0; u < kVoteUnroll; ++u) {
           const uint32_t e = e0 + 32 * u + lane;
-          const size_t idx = (size_t)o + (e < n ? e : n - 1);
           // streaming loads (ld.global.cs, evict-first): bucket tiles must not push the vote rows that the
           // RED.ADDs below keep hitting out of L2
-          a[u] = __ldcs(P.s0 + idx); b[u] = __ldcs(P.s1 + idx); c[u] = __ldcs(P.s2 + idx);
-          f[u] = __ldcs(P.fr + idx);
+          v[u] = __ldcs(P.pack + (size_t)o + (e < n ? e : n - 1));
         }
         for (int p = i; p < i + run; ++p) {
-          const double q0 = sh_s[wid][p][0], q1 = sh_s[wid][p][1], q2 = sh_s[wid][p][2], thr2 = sh_s[wid][p][3];
+          const float q0 = sh_f[wid][p][0], q1 = sh_f[wid][p][1], q2 = sh_f[wid][p][2];
+          const float lo = sh_f[wid][p][3], hi = sh_f[wid][p][4];
           const uint32_t qframe = sh_q[wid][p][1];
           uint32_t *row = P.votes + (size_t)sh_q[wid][p][0] * (size_t)P.F;
+          uint32_t amb = 0;
 #pragma unroll
           for (int u = 0; u < kVoteUnroll; ++u) {
             const uint32_t e = e0 + 32 * u + lane;
-            const double d2 = sqn3(__dsub_rn(q0, a[u]), __dsub_rn(q1, b[u]), __dsub_rn(q2, c[u]));
-            const bool hit = (e < n) && (f[u] + P.frame_lo != qframe) && (d2 < thr2);
-            if (kDoVote && hit) atomicAdd(row + f[u], 1u);
+            const uint32_t f = __float_as_uint(v[u].w);
+            const float dx = q0 - v[u].x, dy = q1 - v[u].y, dz = q2 - v[u].z;
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            const bool live = (e < n) && (f + P.frame_lo != qframe);
+            const bool hit = live && d2 < lo;
+            if (live && !(d2 < lo) && !(d2 > hi)) amb |= 1u << u;  // inside the band (or not comparable)
+            if (kDoVote && hit) atomicAdd(row + f, 1u);
             cM += hit;
           }
+          if (amb) cM += join_exact<kDoVote>(P, sh_s[wid][p], row, o, n, e0 + lane, amb);  // rare
         }
       }
       i += run;
@@ -1151,6 +1187,7 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
         J.pkey = (uint32_t *)(S + o_jk1); J.pval = (uint32_t *)(S + o_jv1); J.npairs = npairs;
         J.q = qb->rec.p; J.aux = aux; J.table = h->table.p;
         J.s0 = h->v_s0.p; J.s1 = h->v_s1.p; J.s2 = h->v_s2.p; J.fr = h->v_frame.p;
+        J.pack = h->v_pack.p; J.band = 2.0e-6 * (1.0 + 1.0 / h->c.rough);
         J.frame_lo = (uint32_t)h->frame_lo(); J.F = Fa; J.votes = r->votes.p;
         J.seg_counter = d_cursor + 1; J.counters = r->counters.p; J.slot_mask = (uint32_t)((1ull << sbits) - 1);
         SGTD_CUDA(h, cudaEventRecord(ev[8], st));
