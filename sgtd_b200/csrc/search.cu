@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
   __shared__ uint32_t sh_q[kVoteThreads / 32][kJoinSeg][2];  // query index, query frame id
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned long long nseg = (P.npairs + kJoinSeg - 1) / kJoinSeg;
-  unsigned long long cM = 0;
+  uint32_t cM = 0;  // per-thread match count (< 2^32: a thread sees a 1/150k share of the batch)
   while (true) {
     unsigned long long seg = 0;
     if (lane == 0) seg = atomicAdd(P.seg_counter, 1ull);
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
       sh_f[wid][lane][0] = (float)r.s[0]; sh_f[wid][lane][1] = (float)r.s[1]; sh_f[wid][lane][2] = (float)r.s[2];
       sh_f[wid][lane][3] = __double2float_rd(a.thr2 * (1.0 - P.band));  // below: certainly a match
       sh_f[wid][lane][4] = __double2float_ru(a.thr2 * (1.0 + P.band));  // above: certainly not
-      sh_q[wid][lane][0] = a.qi; sh_q[wid][lane][1] = r.frame;
+      sh_q[wid][lane][0] = a.qi; sh_q[wid][lane][1] = r.frame - P.frame_lo;
     }
     __syncwarp();
     int i = 0;
@@ -317,22 +317,24 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
           // streaming loads (ld.global.cs, evict-first): bucket tiles must not push the vote rows that the
           // RED.ADDs below keep hitting out of L2
           v[u] = __ldcs(P.pack + (size_t)o + (e < n ? e : n - 1));
+          // tail lanes re-read the last entry: give them a frame id no query can have so they never count
+          if (e >= n) v[u].w = __uint_as_float(0xFFFFFFFFu);
         }
         for (int p = i; p < i + run; ++p) {
           const float q0 = sh_f[wid][p][0], q1 = sh_f[wid][p][1], q2 = sh_f[wid][p][2];
           const float lo = sh_f[wid][p][3], hi = sh_f[wid][p][4];
-          const uint32_t qframe = sh_q[wid][p][1];
+          const uint32_t qfl = sh_q[wid][p][1];  // query frame id relative to this shard (never 0xFFFFFFFF)
           uint32_t *row = P.votes + (size_t)sh_q[wid][p][0] * (size_t)P.F;
           uint32_t amb = 0;
 #pragma unroll
           for (int u = 0; u < kVoteUnroll; ++u) {
-            const uint32_t e = e0 + 32 * u + lane;
             const uint32_t f = __float_as_uint(v[u].w);
             const float dx = q0 - v[u].x, dy = q1 - v[u].y, dz = q2 - v[u].z;
             const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-            const bool live = (e < n) && (f + P.frame_lo != qframe);
+            // (src.frame_id_ - db.frame_id_) > 0 on unsigned == "!=" (STDesc.cpp:373)
+            const bool live = (f != qfl) && (f != 0xFFFFFFFFu);
             const bool hit = live && d2 < lo;
-            if (live && !(d2 < lo) && !(d2 > hi)) amb |= 1u << u;  // inside the band (or not comparable)
+            if (live && d2 >= lo && d2 <= hi) amb |= 1u << u;  // inside the decision band
             if (kDoVote && hit) atomicAdd(row + f, 1u);
             cM += hit;
           }
@@ -342,9 +344,10 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
       i += run;
     }
   }
+  unsigned long long cM64 = cM;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cM += __shfl_xor_sync(0xffffffffu, cM, o);
-  if (lane == 0 && cM) atomicAdd(P.counters + 4, cM);
+  for (int o = 16; o > 0; o >>= 1) cM64 += __shfl_xor_sync(0xffffffffu, cM64, o);
+  if (lane == 0 && cM64) atomicAdd(P.counters + 4, cM64);
 }
 
 // ============================ top-k ==============================================
