@@ -528,6 +528,7 @@ struct CollectParams {
   const DescRec *db; const int64_t *frame_off; const uint64_t *f_key; const uint32_t *f_g;
   const double *f_side;  // side lengths in frame-view (key-sorted) order, 3 per entry
   int64_t frame_lo;
+  int skip_upto;         // candidates with nmatch <= skip_upto were handled by k_collect_inv
   uint32_t *m_q, *m_g; uint8_t *m_cell;
 };
 
@@ -556,6 +557,7 @@ struct KeyFinder {
   }
 };
 
+// (k_collect: per-descriptor formulation, used for candidates with more than kSortCap matches)
 // matches of query descriptor r against a keyframe view: calls emit(ord, g) in
 // (probe ordinal, in-frame position) order
 template <typename Emit>
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
   __shared__ int s_yr[2];
   __shared__ uint32_t s_warp[kCollectThreads / 32];
   const sgtd_candidate c = P.cands[blockIdx.x];
-  if (c.match_off < 0 || c.nmatch <= 0) return;
+  if (c.match_off < 0 || c.nmatch <= P.skip_upto) return;
   const int q = blockIdx.x / P.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t fl = c.frame - P.frame_lo;
@@ -682,6 +684,119 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
       }
     }
     base += total;
+  }
+}
+
+// ---- inverted collect: look the keyframe's entries up in a per-query probe table --------------
+// k_collect walks ~14 probes for each of the query's ~2,000 descriptors (~30k lookups per candidate)
+// although a keyframe only has ~2,400 entries.  The inverted form builds, once per query, an
+// open-addressing multimap  probe key -> (descriptor << 5 | ordinal)  (k_query_index), and a candidate
+// CTA then looks its keyframe's ENTRIES up in it (12x fewer lookups); the matches come out in
+// keyframe order, so they are sorted in shared memory (bitonic, <= kSortCap records) on
+// (descriptor, ordinal, in-frame position) to restore the reference's order.  Candidates with more
+// matches than kSortCap are left to k_collect.
+constexpr int kSortCap = 4096;
+constexpr unsigned long long kQtEmpty = 0xFFFFFFFFFFFFFFFFull;
+
+__global__ void __launch_bounds__(256) k_query_index(const DescRec *q, const QAux *aux, const int64_t *q_off, int q_base,
+                                                     unsigned long long *qt_key, uint32_t *qt_io, uint32_t ts) {
+  const int qi = q_base + blockIdx.x;  // tables are indexed by the query's position inside its group
+  const int64_t q0 = q_off[qi], q1 = q_off[qi + 1];
+  unsigned long long *tk = qt_key + (size_t)blockIdx.x * ts;
+  uint32_t *tv = qt_io + (size_t)blockIdx.x * ts;
+  const uint32_t mask = ts - 1;
+  for (int64_t d = q0 + threadIdx.x; d < q1; d += blockDim.x) {
+    const DescRec r = q[d];
+    uint32_t m = aux[d].mask;
+    const uint32_t il = (uint32_t)(d - q0);
+    while (m) {
+      const int ord = __ffs(m) - 1;
+      m &= m - 1;
+      const unsigned long long key = probe_cell_key(r, ord);
+      uint32_t pos = (uint32_t)mix64(key) & mask;
+      while (atomicCAS(&tk[pos], kQtEmpty, key) != kQtEmpty) pos = (pos + 1) & mask;  // one slot per probe
+      tv[pos] = (il << 5) | (uint32_t)ord;
+    }
+  }
+}
+
+struct CollectInvParams {
+  const sgtd_candidate *cands;
+  int k;
+  const DescRec *q; const QAux *aux; const int64_t *q_off;
+  const unsigned long long *qt_key; const uint32_t *qt_io; uint32_t ts;
+  int q_base;  // first query of the group the tables were built for
+  const int64_t *frame_off; const uint64_t *f_key; const uint32_t *f_g; const double *f_side;
+  int64_t frame_lo;
+  uint32_t *m_q, *m_g; uint8_t *m_cell;
+};
+
+__global__ void __launch_bounds__(kCollectThreads) k_collect_inv(CollectInvParams P) {
+  __shared__ unsigned long long s_key[kSortCap];
+  __shared__ uint32_t s_n;
+  const size_t cslot = (size_t)P.q_base * P.k + blockIdx.x;
+  const sgtd_candidate c = P.cands[cslot];
+  if (c.match_off < 0 || c.nmatch <= 0 || c.nmatch > kSortCap) return;
+  const int q = (int)(cslot / P.k);
+  const int tid = threadIdx.x;
+  const int64_t fl = c.frame - P.frame_lo;
+  const int64_t fo = P.frame_off[fl];
+  const int nf = (int)(P.frame_off[fl + 1] - fo);
+  const int64_t q0 = P.q_off[q];
+  const unsigned long long *tk = P.qt_key + (size_t)(q - P.q_base) * P.ts;
+  const uint32_t *tv = P.qt_io + (size_t)(q - P.q_base) * P.ts;
+  const uint32_t mask = P.ts - 1;
+  int npad = 1;
+  while (npad < c.nmatch) npad <<= 1;
+  if (tid == 0) s_n = 0;
+  for (int i = tid; i < npad; i += kCollectThreads) s_key[i] = kQtEmpty;  // padding sorts last
+  __syncthreads();
+  for (int p = tid; p < nf; p += kCollectThreads) {
+    const unsigned long long key = P.f_key[fo + p];
+    uint32_t pos = (uint32_t)mix64(key) & mask;
+    bool have = false;
+    double e0 = 0, e1 = 0, e2 = 0;
+    while (true) {
+      const unsigned long long kk = __ldg(tk + pos);
+      if (kk == kQtEmpty) break;
+      if (kk == key) {
+        if (!have) { e0 = P.f_side[3 * (fo + p)]; e1 = P.f_side[3 * (fo + p) + 1]; e2 = P.f_side[3 * (fo + p) + 2]; have = true; }
+        const uint32_t io = __ldg(tv + pos);
+        const DescRec r = P.q[q0 + (io >> 5)];
+        if (r.frame != (uint32_t)c.frame) {
+          const double d2 = sqn3(__dsub_rn(r.s[0], e0), __dsub_rn(r.s[1], e1), __dsub_rn(r.s[2], e2));
+          if (d2 < P.aux[q0 + (io >> 5)].thr2) {
+            const uint32_t slot = atomicAdd(&s_n, 1u);
+            if (slot < (uint32_t)kSortCap) {
+              // sort key: descriptor (26 bits) | ordinal (5) | position in the key-sorted view (24) -- equal
+              // keys keep in-frame order in the view, so position order == the reference's bucket order j
+              s_key[slot] = ((unsigned long long)(io >> 5) << 32) | ((unsigned long long)(io & 31u) << 24) | (unsigned long long)p;
+            }
+          }
+        }
+      }
+      pos = (pos + 1) & mask;
+    }
+  }
+  __syncthreads();
+  // bitonic sort of npad (key, value) pairs in shared memory
+  for (int size = 2; size <= npad; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < npad / 2; i += kCollectThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = s_key[lo], b = s_key[hi];
+        if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
+      }
+      __syncthreads();
+    }
+  const int n = (int)min(s_n, (uint32_t)c.nmatch);
+  for (int i = tid; i < n; i += kCollectThreads) {
+    const unsigned long long kk = s_key[i];
+    P.m_q[c.match_off + i] = (uint32_t)(kk >> 32);
+    P.m_cell[c.match_off + i] = (uint8_t)((kk >> 24) & 31u);
+    P.m_g[c.match_off + i] = P.f_g[fo + (int64_t)(kk & 0xFFFFFFull)];
   }
 }
 
@@ -1119,6 +1234,17 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   size_t o_jk1 = o; o += al(npair_cap * 4);
   size_t o_jv0 = o; o += al(npair_cap * 4);
   size_t o_jv1 = o; o += al(npair_cap * 4);
+  // per-query probe multimap for k_collect_inv: 32 slots per descriptor of the largest query (at most 27
+  // probes per descriptor, ~14 on average: load ~0.45, never full)
+  int64_t max_dq = 1;
+  for (int qi2 = 0; qi2 < nq; ++qi2) max_dq = std::max<int64_t>(max_dq, qb->off[qi2 + 1] - qb->off[qi2]);
+  uint32_t qt_ts = 64;
+  while ((int64_t)qt_ts < 32 * max_dq) qt_ts <<= 1;
+  // all queries of the batch in one group: splitting the batch so that the tables stay L2-resident was
+  // measured slower (too little parallelism per launch); SGTD_COLLECT_GROUP overrides for experiments
+  const int qt_group = getenv("SGTD_COLLECT_GROUP") ? std::max(1, atoi(getenv("SGTD_COLLECT_GROUP"))) : std::max(nq, 1);
+  size_t o_qtk = o; o += al((size_t)qt_group * qt_ts * 8);
+  size_t o_qtv = o; o += al((size_t)qt_group * qt_ts * 4);
   size_t o_jc = o; o += al(64);
   size_t o_jcub = o; o += al(cubj);
   SGTD_CUDA(h, h->scratch.reserve(o, st, false));
@@ -1241,10 +1367,31 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   SGTD_CUDA(h, r->m_cell.reserve(tm, st, false)); SGTD_CUDA(h, r->inl.reserve(tm, st, false));
   r->m_q.n = r->m_g.n = r->m_cell.n = r->inl.n = (size_t)total;
   if (total > 0) {
+    const char *cmode = getenv("SGTD_COLLECT_MODE");
+    const bool inverted = !(cmode && strcmp(cmode, "desc") == 0);
+    if (inverted) {
+      // per-query probe multimap, then one lookup per keyframe entry + shared-memory sort
+      CollectInvParams I{};
+      I.cands = r->cands.p; I.k = k; I.q = qb->rec.p; I.aux = aux; I.q_off = qb->d_off.p;
+      I.qt_key = (const unsigned long long *)(S + o_qtk); I.qt_io = (const uint32_t *)(S + o_qtv); I.ts = qt_ts;
+      I.frame_off = h->d_frame_off.p; I.f_key = h->f_key.p; I.f_g = h->f_g.p; I.f_side = h->f_side.p;
+      I.frame_lo = h->frame_lo();
+      I.m_q = r->m_q.p; I.m_g = r->m_g.p; I.m_cell = r->m_cell.p;
+      for (int qb0 = 0; qb0 < nq; qb0 += qt_group) {
+        const int gq = std::min(qt_group, nq - qb0);
+        SGTD_CUDA(h, cudaMemsetAsync(S + o_qtk, 0xFF, (size_t)gq * qt_ts * 8, st));
+        k_query_index<<<gq, 256, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (unsigned long long *)(S + o_qtk),
+                                          (uint32_t *)(S + o_qtv), qt_ts);
+        I.q_base = qb0;
+        k_collect_inv<<<(unsigned)gq * k, kCollectThreads, 0, st>>>(I);
+        h->launches += 2;
+      }
+    }
     CollectParams C{};
     C.cands = r->cands.p; C.k = k; C.q = qb->rec.p; C.aux = aux; C.q_off = qb->d_off.p;
     C.db = h->rec.p; C.frame_off = h->d_frame_off.p; C.f_key = h->f_key.p; C.f_g = h->f_g.p;
     C.f_side = h->f_side.p; C.frame_lo = h->frame_lo();
+    C.skip_upto = inverted ? kSortCap : 0;
     C.m_q = r->m_q.p; C.m_g = r->m_g.p; C.m_cell = r->m_cell.p;
     k_collect<<<(unsigned)nslot, kCollectThreads, 0, st>>>(C);
     SGTD_LAUNCHED(h);
