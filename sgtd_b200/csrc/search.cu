@@ -697,13 +697,16 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
 // matches than kSortCap are left to k_collect.
 constexpr int kSortCap = 4096;
 constexpr unsigned long long kQtEmpty = 0xFFFFFFFFFFFFFFFFull;
+struct __align__(16) QtSlot {  // one probe of a query: key and (descriptor << 5 | ordinal) in one 16-byte sector read
+  unsigned long long key;
+  uint32_t io, pad;
+};
 
 __global__ void __launch_bounds__(256) k_query_index(const DescRec *q, const QAux *aux, const int64_t *q_off, int q_base,
-                                                     unsigned long long *qt_key, uint32_t *qt_io, uint32_t ts) {
+                                                     QtSlot *qt, uint32_t ts) {
   const int qi = q_base + blockIdx.x;  // tables are indexed by the query's position inside its group
   const int64_t q0 = q_off[qi], q1 = q_off[qi + 1];
-  unsigned long long *tk = qt_key + (size_t)blockIdx.x * ts;
-  uint32_t *tv = qt_io + (size_t)blockIdx.x * ts;
+  QtSlot *tk = qt + (size_t)blockIdx.x * ts;
   const uint32_t mask = ts - 1;
   for (int64_t d = q0 + threadIdx.x; d < q1; d += blockDim.x) {
     const DescRec r = q[d];
@@ -714,8 +717,8 @@ __global__ void __launch_bounds__(256) k_query_index(const DescRec *q, const QAu
       m &= m - 1;
       const unsigned long long key = probe_cell_key(r, ord);
       uint32_t pos = (uint32_t)mix64(key) & mask;
-      while (atomicCAS(&tk[pos], kQtEmpty, key) != kQtEmpty) pos = (pos + 1) & mask;  // one slot per probe
-      tv[pos] = (il << 5) | (uint32_t)ord;
+      while (atomicCAS(&tk[pos].key, kQtEmpty, key) != kQtEmpty) pos = (pos + 1) & mask;  // one slot per probe
+      tk[pos].io = (il << 5) | (uint32_t)ord;
     }
   }
 }
@@ -724,7 +727,7 @@ struct CollectInvParams {
   const sgtd_candidate *cands;
   int k;
   const DescRec *q; const QAux *aux; const int64_t *q_off;
-  const unsigned long long *qt_key; const uint32_t *qt_io; uint32_t ts;
+  const QtSlot *qt; uint32_t ts;
   int q_base;  // first query of the group the tables were built for
   const int64_t *frame_off; const uint64_t *f_key; const uint32_t *f_g; const double *f_side;
   int64_t frame_lo;
@@ -743,8 +746,7 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect_inv(CollectInvParam
   const int64_t fo = P.frame_off[fl];
   const int nf = (int)(P.frame_off[fl + 1] - fo);
   const int64_t q0 = P.q_off[q];
-  const unsigned long long *tk = P.qt_key + (size_t)(q - P.q_base) * P.ts;
-  const uint32_t *tv = P.qt_io + (size_t)(q - P.q_base) * P.ts;
+  const QtSlot *tk = P.qt + (size_t)(q - P.q_base) * P.ts;
   const uint32_t mask = P.ts - 1;
   int npad = 1;
   while (npad < c.nmatch) npad <<= 1;
@@ -757,11 +759,12 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect_inv(CollectInvParam
     bool have = false;
     double e0 = 0, e1 = 0, e2 = 0;
     while (true) {
-      const unsigned long long kk = __ldg(tk + pos);
+      const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(tk + pos));
+      const unsigned long long kk = ((unsigned long long)raw.y << 32) | raw.x;
       if (kk == kQtEmpty) break;
       if (kk == key) {
         if (!have) { e0 = P.f_side[3 * (fo + p)]; e1 = P.f_side[3 * (fo + p) + 1]; e2 = P.f_side[3 * (fo + p) + 2]; have = true; }
-        const uint32_t io = __ldg(tv + pos);
+        const uint32_t io = raw.z;
         const DescRec r = P.q[q0 + (io >> 5)];
         if (r.frame != (uint32_t)c.frame) {
           const double d2 = sqn3(__dsub_rn(r.s[0], e0), __dsub_rn(r.s[1], e1), __dsub_rn(r.s[2], e2));
@@ -1243,8 +1246,7 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   // all queries of the batch in one group: splitting the batch so that the tables stay L2-resident was
   // measured slower (too little parallelism per launch); SGTD_COLLECT_GROUP overrides for experiments
   const int qt_group = getenv("SGTD_COLLECT_GROUP") ? std::max(1, atoi(getenv("SGTD_COLLECT_GROUP"))) : std::max(nq, 1);
-  size_t o_qtk = o; o += al((size_t)qt_group * qt_ts * 8);
-  size_t o_qtv = o; o += al((size_t)qt_group * qt_ts * 4);
+  size_t o_qtk = o; o += al((size_t)qt_group * qt_ts * 16);
   size_t o_jc = o; o += al(64);
   size_t o_jcub = o; o += al(cubj);
   SGTD_CUDA(h, h->scratch.reserve(o, st, false));
@@ -1376,15 +1378,14 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
       // per-query probe multimap, then one lookup per keyframe entry + shared-memory sort
       CollectInvParams I{};
       I.cands = r->cands.p; I.k = k; I.q = qb->rec.p; I.aux = aux; I.q_off = qb->d_off.p;
-      I.qt_key = (const unsigned long long *)(S + o_qtk); I.qt_io = (const uint32_t *)(S + o_qtv); I.ts = qt_ts;
+      I.qt = (const QtSlot *)(S + o_qtk); I.ts = qt_ts;
       I.frame_off = h->d_frame_off.p; I.f_key = h->f_key.p; I.f_g = h->f_g.p; I.f_side = h->f_side.p;
       I.frame_lo = h->frame_lo();
       I.m_q = r->m_q.p; I.m_g = r->m_g.p; I.m_cell = r->m_cell.p;
       for (int qb0 = 0; qb0 < nq; qb0 += qt_group) {
         const int gq = std::min(qt_group, nq - qb0);
-        SGTD_CUDA(h, cudaMemsetAsync(S + o_qtk, 0xFF, (size_t)gq * qt_ts * 8, st));
-        k_query_index<<<gq, 256, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (unsigned long long *)(S + o_qtk),
-                                          (uint32_t *)(S + o_qtv), qt_ts);
+        SGTD_CUDA(h, cudaMemsetAsync(S + o_qtk, 0xFF, (size_t)gq * qt_ts * sizeof(QtSlot), st));
+        k_query_index<<<gq, 256, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (QtSlot *)(S + o_qtk), qt_ts);
         I.q_base = qb0;
         k_collect_inv<<<(unsigned)gq * k, kCollectThreads, 0, st>>>(I);
         h->launches += 2;
