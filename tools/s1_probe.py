@@ -1,9 +1,8 @@
-"""Stage-1 timing probe (debug helper): batch of synthetic scans, GPU vs oracle."""
+"""Stage-1 timing probe (debug helper): a batch of synthetic scans through sgtd_extract_instances_batch."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sgtd_b200 import capi, synth_scan
-from oracle import orc
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 base = [synth_scan.make_scan(5000 + s) for s in range(8)]
 scans = [base[s % 8] for s in range(ns)]
@@ -14,6 +13,3 @@ for it in range(3):
     t0 = time.perf_counter(); nodes, noff, pi, ninst = m.extract_instances(P, L, off); dt = time.perf_counter() - t0
     print(f"gpu batch {ns} scans: {dt*1e3:.1f} ms -> {ns/dt:.1f} scans/s, nodes/scan {len(nodes)/ns:.1f}")
 t0 = time.perf_counter(); nodes, noff, pi, ninst = m.extract_instances(*base[0]); print("gpu single scan %.1f ms" % ((time.perf_counter()-t0)*1e3))
-t0 = time.perf_counter()
-for p, l in base: orc.extract_instances(p, l)
-print("oracle %.1f ms/scan" % ((time.perf_counter()-t0)*1e3/8))
