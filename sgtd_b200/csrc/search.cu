@@ -1091,8 +1091,9 @@ __global__ void __launch_bounds__(kVerifyThreads) k_verify(VerifyParams P) {
         const float dB = resid2_f32(Rf, tf, v0.w, v1.x, v1.y, v3.x, v3.y, v3.z);
         const float dC = resid2_f32(Rf, tf, v1.z, v1.w, v2.x, v3.w, v4.x, v4.y);
         const float lo = 9.0f - margin, hi = 9.0f + margin;
-        if (dA < lo && dB < lo && dC < lo) { ++vote; continue; }  // clearly an inlier
-        if (dA > hi || dB > hi || dC > hi) continue;              // clearly not
+        const float m3 = fmaxf(dA, fmaxf(dB, dC));  // finite for finite coordinates
+        if (m3 < lo) { ++vote; continue; }  // all three clearly inside: an inlier
+        if (m3 > hi) continue;              // some vertex clearly outside
         // some vertex is inside the band (or not comparable): decide it exactly
         const bool ok = vertex_inlier_fast(Rf, tf, R, t, v0.x, v0.y, v0.z, v2.y, v2.z, v2.w, margin) &&
                         vertex_inlier_fast(Rf, tf, R, t, v0.w, v1.x, v1.y, v3.x, v3.y, v3.z, margin) &&
