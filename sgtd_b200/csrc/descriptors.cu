@@ -92,7 +92,6 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_pass1(BuildParams P) {
   const int tid = threadIdx.x;
   unsigned long long *slot_key = P.slot_key + (size_t)blockIdx.x * P.slots_per_cta;
   uint32_t *slot_seq = P.slot_seq + (size_t)blockIdx.x * P.slots_per_cta;
-  const uint32_t mask = P.slots_per_cta - 1;
 
   for (int s = blockIdx.x; s < P.nscans; s += gridDim.x) {
     const int64_t n0 = P.node_off[s];
@@ -110,7 +109,6 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_pass1(BuildParams P) {
     while (tsz < 2u * (uint32_t)T && tsz < P.slots_per_cta) tsz <<= 1;
     const uint32_t tmask = tsz - 1;
     for (uint32_t i = tid; i < tsz; i += kBuildThreads) { slot_key[i] = SGTD_EMPTY_KEY; slot_seq[i] = 0xFFFFFFFFu; }
-    (void)mask;
     __syncthreads();
     // ---- exact kNN: FLANN L2_Simple<float> order (dx*dx + dy*dy) + dz*dz, ties -> lower index
     for (int i = tid; i < K; i += kBuildThreads) {

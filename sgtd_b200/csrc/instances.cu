@@ -308,7 +308,6 @@ __global__ void __launch_bounds__(32) k_dcvc_replay(S1Buffers B) {
   const int lane = threadIdx.x;
   const TaskState ts = B.ts[blockIdx.x];
   const int height = ts.height;
-  const int *t_min1 = B.t_min1 + t.tab_off, *t_min2 = B.t_min2 + t.tab_off;
   int *t_kind = B.t_kind + t.tab_off, *t_label = B.t_label + t.tab_off;
   UnionFind uf{s_parent, B.parent + t.lab_off};
   int *pt_label = B.pt_label + t.idx_off;

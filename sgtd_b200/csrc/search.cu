@@ -1036,8 +1036,20 @@ __device__ __forceinline__ bool vertex_inlier_fast(const float *Rf, const float 
   return sqn3(dx, dy, dz) < 9.0;
 }
 
+// Two pairs per instruction: Blackwell's packed FP32 (FFMA2/FADD2/FMUL2) halves the FMA-pipe
+// issue slots of the pre-filter, which is what bounds this kernel.  Each half is an IEEE fmaf,
+// so the values equal resid2_f32()'s.  nb* hold the NEGATED keyframe coordinates.
+__device__ __forceinline__ float2 resid2_x2(const float2 *R2, const float2 *t2, float2 px, float2 py, float2 pz,
+                                            float2 nbx, float2 nby, float2 nbz) {
+  const float2 rx = __fadd2_rn(__ffma2_rn(R2[0], px, __ffma2_rn(R2[1], py, __ffma2_rn(R2[2], pz, t2[0]))), nbx);
+  const float2 ry = __fadd2_rn(__ffma2_rn(R2[3], px, __ffma2_rn(R2[4], py, __ffma2_rn(R2[5], pz, t2[1]))), nby);
+  const float2 rz = __fadd2_rn(__ffma2_rn(R2[6], px, __ffma2_rn(R2[7], py, __ffma2_rn(R2[8], pz, t2[2]))), nbz);
+  return __ffma2_rn(rx, rx, __ffma2_rn(ry, ry, __fmul2_rn(rz, rz)));
+}
+constexpr int kCoupleStride = 40;  // floats per staged couple of pairs: 18 float2 coordinates, float2 margin, pad
+
 __global__ void __launch_bounds__(kVerifyThreads) k_verify(VerifyParams P) {
-  __shared__ PairTile s_pair[kVerifyThreads];
+  __shared__ __align__(16) float s_tile[(kVerifyThreads / 2) * kCoupleStride];
   __shared__ int s_vote[kVerifyThreads];
   __shared__ double s_pose[12];
   __shared__ int s_best, s_wcnt[2];
@@ -1061,45 +1073,70 @@ __global__ void __launch_bounds__(kVerifyThreads) k_verify(VerifyParams P) {
   for (int i = 0; i < 9; ++i) Rf[i] = (tid < H) ? (float)R[i] : 0.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) { tf[i] = (tid < H) ? (float)t[i] : 0.f; tmax = fmaxf(tmax, fabsf(tf[i])); }
+  float2 R2[9], t2[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R2[i] = make_float2(Rf[i], Rf[i]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t2[i] = make_float2(tf[i], tf[i]);
   const float mt = fminf(fmaf(4.0e-5f, tmax, 1.0e-4f), 8.0f);
   int vote = 0;
   for (int jb = 0; jb < M; jb += kVerifyThreads) {
     const int nt = min(kVerifyThreads, M - jb);
     __syncthreads();
+    // stage the tile couple-interleaved: float2 k of couple c = coordinate k of pairs 2c (.x) and 2c+1 (.y)
     if (tid < nt) {
       float a[9], b[9];
       load_pair(P, q0, moff + jb + tid, a, b);
       float mx = 0.f;
 #pragma unroll
       for (int i = 0; i < 9; ++i) mx = fmaxf(mx, fmaxf(fabsf(a[i]), fabsf(b[i])));
-      PairTile pt;
-      pt.v[0] = make_float4(a[0], a[1], a[2], a[3]); pt.v[1] = make_float4(a[4], a[5], a[6], a[7]);
-      pt.v[2] = make_float4(a[8], b[0], b[1], b[2]); pt.v[3] = make_float4(b[3], b[4], b[5], b[6]);
-      pt.v[4] = make_float4(b[7], b[8], fminf(fmaf(4.0e-5f, mx, 1.0e-4f), 8.0f), 0.f);  // .z = margin of the pair
-      s_pair[tid] = pt;
+      float *dst = s_tile + (tid >> 1) * kCoupleStride + (tid & 1);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { dst[2 * i] = a[i]; dst[2 * (9 + i)] = -b[i]; }
+      dst[36] = fminf(fmaf(4.0e-5f, mx, 1.0e-4f), 8.0f);  // margin of the pair
+    } else if (tid == nt && (nt & 1)) {
+      // odd tail: the missing half is a pair at infinity (residual +inf: never an inlier, never ambiguous)
+      float *dst = s_tile + (tid >> 1) * kCoupleStride + 1;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { dst[2 * i] = 0.f; dst[2 * (9 + i)] = -__int_as_float(0x7f800000); }
+      dst[36] = 0.f;
     }
     __syncthreads();
-    if (tid < H)
-      for (int jj = 0; jj < nt; ++jj) {
-        const float4 v0 = s_pair[jj].v[0], v1 = s_pair[jj].v[1], v2 = s_pair[jj].v[2], v3 = s_pair[jj].v[3],
-                     v4 = s_pair[jj].v[4];
-        // margin(X) = 16 * 40 * eps32 * X (+ slack), X = max |coordinate| of the pair and |t|;
-        // v4.z already holds the pair's margin, mt this hypothesis' own
-        const float margin = fmaxf(v4.z, mt);
-        // straight-line FP32 residuals of the three vertices (independent FMA chains)
-        const float dA = resid2_f32(Rf, tf, v0.x, v0.y, v0.z, v2.y, v2.z, v2.w);
-        const float dB = resid2_f32(Rf, tf, v0.w, v1.x, v1.y, v3.x, v3.y, v3.z);
-        const float dC = resid2_f32(Rf, tf, v1.z, v1.w, v2.x, v3.w, v4.x, v4.y);
+    if (tid < H) {
+      const int nc = (nt + 1) >> 1;
+      for (int c = 0; c < nc; ++c) {
+        const float4 *tc = reinterpret_cast<const float4 *>(s_tile + c * kCoupleStride);
+        const float4 w0 = tc[0], w1 = tc[1], w2 = tc[2], w3 = tc[3], w4 = tc[4], w5 = tc[5], w6 = tc[6], w7 = tc[7],
+                     w8 = tc[8];
+        const float2 mg = *reinterpret_cast<const float2 *>(s_tile + c * kCoupleStride + 36);
+#define SGTD_LO(q4) make_float2((q4).x, (q4).y)
+#define SGTD_HI(q4) make_float2((q4).z, (q4).w)
+        // coordinate k lives in w[k/2] (low half for even k): a0..a8 = k 0..8, -b0..-b8 = k 9..17
+        const float2 dA = resid2_x2(R2, t2, SGTD_LO(w0), SGTD_HI(w0), SGTD_LO(w1), SGTD_HI(w4), SGTD_LO(w5), SGTD_HI(w5));
+        const float2 dB = resid2_x2(R2, t2, SGTD_HI(w1), SGTD_LO(w2), SGTD_HI(w2), SGTD_LO(w6), SGTD_HI(w6), SGTD_LO(w7));
+        const float2 dC = resid2_x2(R2, t2, SGTD_LO(w3), SGTD_HI(w3), SGTD_LO(w4), SGTD_HI(w7), SGTD_LO(w8), SGTD_HI(w8));
+        // margin(X) = 16 * 40 * eps32 * X (+ slack), X = max |coordinate| of the pairs and |t|
+        const float margin = fmaxf(fmaxf(mg.x, mg.y), mt);
         const float lo = 9.0f - margin, hi = 9.0f + margin;
-        const float m3 = fmaxf(dA, fmaxf(dB, dC));  // finite for finite coordinates
-        if (m3 < lo) { ++vote; continue; }  // all three clearly inside: an inlier
-        if (m3 > hi) continue;              // some vertex clearly outside
-        // some vertex is inside the band (or not comparable): decide it exactly
-        const bool ok = vertex_inlier_fast(Rf, tf, R, t, v0.x, v0.y, v0.z, v2.y, v2.z, v2.w, margin) &&
-                        vertex_inlier_fast(Rf, tf, R, t, v0.w, v1.x, v1.y, v3.x, v3.y, v3.z, margin) &&
-                        vertex_inlier_fast(Rf, tf, R, t, v1.z, v1.w, v2.x, v3.w, v4.x, v4.y, margin);
-        vote += ok;
+        const float m0 = fmaxf(dA.x, fmaxf(dB.x, dC.x)), m1 = fmaxf(dA.y, fmaxf(dB.y, dC.y));
+        const bool in0 = m0 < lo, in1 = m1 < lo;  // all three vertices clearly inside: an inlier
+        vote += (int)in0 + (int)in1;
+        const bool amb0 = !(in0 || m0 > hi), amb1 = !(in1 || m1 > hi);
+        if (amb0 || amb1) {
+          // some vertex is inside the band (or not comparable): decide that pair exactly
+          if (amb0)
+            vote += vertex_inlier_fast(Rf, tf, R, t, w0.x, w0.z, w1.x, -w4.z, -w5.x, -w5.z, margin) &&
+                    vertex_inlier_fast(Rf, tf, R, t, w1.z, w2.x, w2.z, -w6.x, -w6.z, -w7.x, margin) &&
+                    vertex_inlier_fast(Rf, tf, R, t, w3.x, w3.z, w4.x, -w7.z, -w8.x, -w8.z, margin);
+          if (amb1)
+            vote += vertex_inlier_fast(Rf, tf, R, t, w0.y, w0.w, w1.y, -w4.w, -w5.y, -w5.w, margin) &&
+                    vertex_inlier_fast(Rf, tf, R, t, w1.w, w2.y, w2.w, -w6.y, -w6.w, -w7.y, margin) &&
+                    vertex_inlier_fast(Rf, tf, R, t, w3.y, w3.w, w4.y, -w7.w, -w8.y, -w8.w, margin);
+        }
+#undef SGTD_LO
+#undef SGTD_HI
       }
+    }
   }
   s_vote[tid] = (tid < H) ? vote : -1;
   __syncthreads();
