@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect_inv(CollectInvParam
 }
 
 // ============================ verification ===========================================
-constexpr int kVerifyThreads = 64;
+constexpr int kVerifyThreads = 128;
 
 struct Rot2 { double c, s; };
 __device__ __forceinline__ Rot2 rot_t(Rot2 j) { Rot2 r; r.c = j.c; r.s = -j.s; return r; }
@@ -999,10 +999,13 @@ __device__ __forceinline__ void load_pair(const VerifyParams &P, int64_t q0, int
   b[0] = y.a.x; b[1] = y.a.y; b[2] = y.a.z; b[3] = y.b.x; b[4] = y.b.y; b[5] = y.b.z; b[6] = y.c.x; b[7] = y.c.y; b[8] = y.c.z;
 }
 
-// One CTA (2 warps) per candidate.  Thread h owns hypothesis h (<= 50): it solves
-// the 3-point Kabsch of pair h*skip and keeps (R,t) in registers.  Match pairs
-// are staged 64 at a time in shared memory; every hypothesis thread walks the
-// tile with broadcast reads, so each pair is fetched from HBM/L2 once per pass.
+// One CTA (4 warps) per candidate.  Threads 0..H-1 first solve the 3-point Kabsch of pair
+// h*skip (H <= 49 hypotheses) and park (R,t) in shared memory.  Then the roles are transposed:
+// a thread owns a couple of match pairs (registers, fetched once from HBM/L2) and walks the
+// hypotheses with broadcast shared-memory reads -- every lane is busy whatever H is, and
+// there is no barrier inside the scoring loop.  Votes are warp-ballot counts; the per-pair
+// outcome bits of all hypotheses are kept (64-bit mask per pair, shared memory) so that the
+// inlier list of the winning hypothesis needs no second evaluation.
 //
 // Hypothesis votes use an FP32 pre-filter: the residual of each vertex is first formed
 // in float (FMA).  With |coordinate|, |t| <= X the float residual components are off by
@@ -1036,109 +1039,154 @@ __device__ __forceinline__ bool vertex_inlier_fast(const float *Rf, const float 
   return sqn3(dx, dy, dz) < 9.0;
 }
 
-// Two pairs per instruction: Blackwell's packed FP32 (FFMA2/FADD2/FMUL2) halves the FMA-pipe
-// issue slots of the pre-filter, which is what bounds this kernel.  Each half is an IEEE fmaf,
-// so the values equal resid2_f32()'s.  nb* hold the NEGATED keyframe coordinates.
-__device__ __forceinline__ float2 resid2_x2(const float2 *R2, const float2 *t2, float2 px, float2 py, float2 pz,
-                                            float2 nbx, float2 nby, float2 nbz) {
-  const float2 rx = __fadd2_rn(__ffma2_rn(R2[0], px, __ffma2_rn(R2[1], py, __ffma2_rn(R2[2], pz, t2[0]))), nbx);
-  const float2 ry = __fadd2_rn(__ffma2_rn(R2[3], px, __ffma2_rn(R2[4], py, __ffma2_rn(R2[5], pz, t2[1]))), nby);
-  const float2 rz = __fadd2_rn(__ffma2_rn(R2[6], px, __ffma2_rn(R2[7], py, __ffma2_rn(R2[8], pz, t2[2]))), nbz);
-  return __ffma2_rn(rx, rx, __ffma2_rn(ry, ry, __fmul2_rn(rz, rz)));
+// Two pairs per instruction: Blackwell's packed FP32 (FFMA2/FADD2/FMUL2) halves the issue
+// slots of the pre-filter.  Each half is an IEEE fmaf, so the values equal resid2_f32()'s.
+// The packed operands are kept as 64-bit registers (inline PTX) so that the pair coordinates
+// stay in aligned register pairs across the hypothesis loop instead of being re-packed.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
 }
-constexpr int kCoupleStride = 40;  // floats per staged couple of pairs: 18 float2 coordinates, float2 margin, pad
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 resid2_x2(const f32x2 *R2, const f32x2 *t2, f32x2 px, f32x2 py, f32x2 pz, f32x2 bx,
+                                           f32x2 by, f32x2 bz) {
+  const f32x2 rx = sub2(fma2(R2[0], px, fma2(R2[1], py, fma2(R2[2], pz, t2[0]))), bx);
+  const f32x2 ry = sub2(fma2(R2[3], px, fma2(R2[4], py, fma2(R2[5], pz, t2[1]))), by);
+  const f32x2 rz = sub2(fma2(R2[6], px, fma2(R2[7], py, fma2(R2[8], pz, t2[2]))), bz);
+  return fma2(rx, rx, fma2(ry, ry, mul2(rz, rz)));
+}
+constexpr int kMaxHyp = 50;      // hypotheses per candidate (STDesc.cpp:486-489: skip_len = M / 50 + 1 => H <= 49)
+constexpr int kMaskCap = 2560;   // pairs whose outcome masks fit in shared memory; beyond it pass 2 re-evaluates
 
-__global__ void __launch_bounds__(kVerifyThreads) k_verify(VerifyParams P) {
-  __shared__ __align__(16) float s_tile[(kVerifyThreads / 2) * kCoupleStride];
-  __shared__ int s_vote[kVerifyThreads];
-  __shared__ double s_pose[12];
-  __shared__ int s_best, s_wcnt[2];
+__global__ void __launch_bounds__(kVerifyThreads, 5) k_verify(VerifyParams P) {
+  __shared__ __align__(16) double s_pose[kMaxHyp][12];  // exact (R,t) of every hypothesis
+  __shared__ __align__(16) float s_posef[kMaxHyp][16];  // rounded to float: R0..R8, t0..t2, margin(|t|), pad
+  __shared__ unsigned long long s_mask[kMaskCap];       // bit h of s_mask[j]: pair j is an inlier of hypothesis h
+  __shared__ int s_vote[kMaxHyp];
+  __shared__ int s_best, s_cnt[64 * (kVerifyThreads / 32) + 1];
   sgtd_candidate *cd = P.cands + blockIdx.x;
   const int64_t moff = cd->match_off;
   const int M = cd->nmatch;
   if (moff < 0 || M <= 0) return;
   const int q = blockIdx.x / P.k;
   const int64_t q0 = P.q_off[q];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int skip = M / 50 + 1;
   const int H = M / skip;
-  double R[9], t[3];
   if (tid < H) {
     float a[9], b[9];
+    double R[9], t[3];
     load_pair(P, q0, moff + (int64_t)tid * skip, a, b);
     kabsch3(a, b, R, t);
+    float tmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { s_pose[tid][i] = R[i]; s_posef[tid][i] = (float)R[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      s_pose[tid][9 + i] = t[i]; s_posef[tid][9 + i] = (float)t[i]; tmax = fmaxf(tmax, fabsf((float)t[i]));
+    }
+    s_posef[tid][12] = fminf(fmaf(4.0e-5f, tmax, 1.0e-4f), 8.0f);
+    s_vote[tid] = 0;
   }
-  float Rf[9], tf[3], tmax = 0.f;
+  __syncthreads();
+  // ---- pass 1: votes of every hypothesis
+  const int ncouple = (M + 1) >> 1;
+  int acc0 = 0, acc1 = 0;  // lane l of a warp accumulates the warp's votes of hypotheses l and l+32
+  for (int c0 = wid * 32; c0 < ncouple; c0 += kVerifyThreads) {
+    const int c = c0 + lane;
+    // coordinate k of pairs 2c (.x) and 2c+1 (.y): a0..a8 = k 0..8, b0..b8 = k 9..17
+    f32x2 K[18];
+    float mgc = 0.f;
+    const f32x2 negzero2 = pack2(-0.f, -0.f);
+    {
+      float a[9], b[9], a1[9], b1[9];
+      const bool v0 = 2 * c < M, v1 = 2 * c + 1 < M;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) Rf[i] = (tid < H) ? (float)R[i] : 0.f;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { tf[i] = (tid < H) ? (float)t[i] : 0.f; tmax = fmaxf(tmax, fabsf(tf[i])); }
-  float2 R2[9], t2[3];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) R2[i] = make_float2(Rf[i], Rf[i]);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) t2[i] = make_float2(tf[i], tf[i]);
-  const float mt = fminf(fmaf(4.0e-5f, tmax, 1.0e-4f), 8.0f);
-  int vote = 0;
-  for (int jb = 0; jb < M; jb += kVerifyThreads) {
-    const int nt = min(kVerifyThreads, M - jb);
-    __syncthreads();
-    // stage the tile couple-interleaved: float2 k of couple c = coordinate k of pairs 2c (.x) and 2c+1 (.y)
-    if (tid < nt) {
-      float a[9], b[9];
-      load_pair(P, q0, moff + jb + tid, a, b);
+      for (int i = 0; i < 9; ++i) { a[i] = 0.f; a1[i] = 0.f; b[i] = b1[i] = __int_as_float(0x7f800000); }
+      // a missing pair sits at infinity: residual +inf, never an inlier, never ambiguous
+      if (v0) load_pair(P, q0, moff + 2 * c, a, b);
+      if (v1) load_pair(P, q0, moff + 2 * c + 1, a1, b1);
       float mx = 0.f;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) mx = fmaxf(mx, fmaxf(fabsf(a[i]), fabsf(b[i])));
-      float *dst = s_tile + (tid >> 1) * kCoupleStride + (tid & 1);
-#pragma unroll
-      for (int i = 0; i < 9; ++i) { dst[2 * i] = a[i]; dst[2 * (9 + i)] = -b[i]; }
-      dst[36] = fminf(fmaf(4.0e-5f, mx, 1.0e-4f), 8.0f);  // margin of the pair
-    } else if (tid == nt && (nt & 1)) {
-      // odd tail: the missing half is a pair at infinity (residual +inf: never an inlier, never ambiguous)
-      float *dst = s_tile + (tid >> 1) * kCoupleStride + 1;
-#pragma unroll
-      for (int i = 0; i < 9; ++i) { dst[2 * i] = 0.f; dst[2 * (9 + i)] = -__int_as_float(0x7f800000); }
-      dst[36] = 0.f;
-    }
-    __syncthreads();
-    if (tid < H) {
-      const int nc = (nt + 1) >> 1;
-      for (int c = 0; c < nc; ++c) {
-        const float4 *tc = reinterpret_cast<const float4 *>(s_tile + c * kCoupleStride);
-        const float4 w0 = tc[0], w1 = tc[1], w2 = tc[2], w3 = tc[3], w4 = tc[4], w5 = tc[5], w6 = tc[6], w7 = tc[7],
-                     w8 = tc[8];
-        const float2 mg = *reinterpret_cast<const float2 *>(s_tile + c * kCoupleStride + 36);
-#define SGTD_LO(q4) make_float2((q4).x, (q4).y)
-#define SGTD_HI(q4) make_float2((q4).z, (q4).w)
-        // coordinate k lives in w[k/2] (low half for even k): a0..a8 = k 0..8, -b0..-b8 = k 9..17
-        const float2 dA = resid2_x2(R2, t2, SGTD_LO(w0), SGTD_HI(w0), SGTD_LO(w1), SGTD_HI(w4), SGTD_LO(w5), SGTD_HI(w5));
-        const float2 dB = resid2_x2(R2, t2, SGTD_HI(w1), SGTD_LO(w2), SGTD_HI(w2), SGTD_LO(w6), SGTD_HI(w6), SGTD_LO(w7));
-        const float2 dC = resid2_x2(R2, t2, SGTD_LO(w3), SGTD_HI(w3), SGTD_LO(w4), SGTD_HI(w7), SGTD_LO(w8), SGTD_HI(w8));
-        // margin(X) = 16 * 40 * eps32 * X (+ slack), X = max |coordinate| of the pairs and |t|
-        const float margin = fmaxf(fmaxf(mg.x, mg.y), mt);
-        const float lo = 9.0f - margin, hi = 9.0f + margin;
-        const float m0 = fmaxf(dA.x, fmaxf(dB.x, dC.x)), m1 = fmaxf(dA.y, fmaxf(dB.y, dC.y));
-        const bool in0 = m0 < lo, in1 = m1 < lo;  // all three vertices clearly inside: an inlier
-        vote += (int)in0 + (int)in1;
-        const bool amb0 = !(in0 || m0 > hi), amb1 = !(in1 || m1 > hi);
-        if (amb0 || amb1) {
-          // some vertex is inside the band (or not comparable): decide that pair exactly
-          if (amb0)
-            vote += vertex_inlier_fast(Rf, tf, R, t, w0.x, w0.z, w1.x, -w4.z, -w5.x, -w5.z, margin) &&
-                    vertex_inlier_fast(Rf, tf, R, t, w1.z, w2.x, w2.z, -w6.x, -w6.z, -w7.x, margin) &&
-                    vertex_inlier_fast(Rf, tf, R, t, w3.x, w3.z, w4.x, -w7.z, -w8.x, -w8.z, margin);
-          if (amb1)
-            vote += vertex_inlier_fast(Rf, tf, R, t, w0.y, w0.w, w1.y, -w4.w, -w5.y, -w5.w, margin) &&
-                    vertex_inlier_fast(Rf, tf, R, t, w1.w, w2.y, w2.w, -w6.y, -w6.w, -w7.y, margin) &&
-                    vertex_inlier_fast(Rf, tf, R, t, w3.y, w3.w, w4.y, -w7.w, -w8.y, -w8.w, margin);
-        }
-#undef SGTD_LO
-#undef SGTD_HI
+      for (int i = 0; i < 9; ++i) {
+        // "+ (-0)" is the identity on every float; it makes the pair the result of a packed
+        // instruction, which pins it in an aligned register pair for the whole hypothesis loop
+        // (a plain mov.b64 is copy-propagated by ptxas and re-packed in every iteration)
+        K[i] = add2(pack2(a[i], a1[i]), negzero2); K[9 + i] = add2(pack2(b[i], b1[i]), negzero2);
+        if (v0) mx = fmaxf(mx, fmaxf(fabsf(a[i]), fabsf(b[i])));
+        if (v1) mx = fmaxf(mx, fmaxf(fabsf(a1[i]), fabsf(b1[i])));
       }
+      mgc = fminf(fmaf(4.0e-5f, mx, 1.0e-4f), 8.0f);  // margin of the couple
     }
+    unsigned long long mk0 = 0ull, mk1 = 0ull;
+    for (int h = 0; h < H; ++h) {
+      const float4 p0 = *reinterpret_cast<const float4 *>(&s_posef[h][0]), p1 = *reinterpret_cast<const float4 *>(&s_posef[h][4]),
+                   p2 = *reinterpret_cast<const float4 *>(&s_posef[h][8]);
+      const float mt = s_posef[h][12];
+      f32x2 R2[9], t2[3];
+      R2[0] = pack2(p0.x, p0.x); R2[1] = pack2(p0.y, p0.y); R2[2] = pack2(p0.z, p0.z);
+      R2[3] = pack2(p0.w, p0.w); R2[4] = pack2(p1.x, p1.x); R2[5] = pack2(p1.y, p1.y);
+      R2[6] = pack2(p1.z, p1.z); R2[7] = pack2(p1.w, p1.w); R2[8] = pack2(p2.x, p2.x);
+      t2[0] = pack2(p2.y, p2.y); t2[1] = pack2(p2.z, p2.z); t2[2] = pack2(p2.w, p2.w);
+      float2 dA, dB, dC;
+      unpack2(resid2_x2(R2, t2, K[0], K[1], K[2], K[9], K[10], K[11]), dA.x, dA.y);
+      unpack2(resid2_x2(R2, t2, K[3], K[4], K[5], K[12], K[13], K[14]), dB.x, dB.y);
+      unpack2(resid2_x2(R2, t2, K[6], K[7], K[8], K[15], K[16], K[17]), dC.x, dC.y);
+      // margin(X) = 16 * 40 * eps32 * X (+ slack), X = max |coordinate| of the pairs and |t|
+      const float margin = fmaxf(mgc, mt);
+      const float lo = 9.0f - margin, hi = 9.0f + margin;
+      const float m0 = fmaxf(dA.x, fmaxf(dB.x, dC.x)), m1 = fmaxf(dA.y, fmaxf(dB.y, dC.y));
+      bool in0 = m0 < lo, in1 = m1 < lo;  // all three vertices clearly inside: an inlier
+      const bool amb0 = !(in0 || m0 > hi), amb1 = !(in1 || m1 > hi);
+      if (amb0 || amb1) {
+        // some vertex is inside the band (or not comparable): decide that pair exactly
+        const float Rf[9] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x};
+        const float tf[3] = {p2.y, p2.z, p2.w};
+        const double *R = &s_pose[h][0], *t = &s_pose[h][9];
+        float u[18], v[18];  // pair 2c, pair 2c+1
+#pragma unroll
+        for (int i = 0; i < 18; ++i) unpack2(K[i], u[i], v[i]);
+        if (amb0)
+          in0 = vertex_inlier_fast(Rf, tf, R, t, u[0], u[1], u[2], u[9], u[10], u[11], margin) &&
+                vertex_inlier_fast(Rf, tf, R, t, u[3], u[4], u[5], u[12], u[13], u[14], margin) &&
+                vertex_inlier_fast(Rf, tf, R, t, u[6], u[7], u[8], u[15], u[16], u[17], margin);
+        if (amb1)
+          in1 = vertex_inlier_fast(Rf, tf, R, t, v[0], v[1], v[2], v[9], v[10], v[11], margin) &&
+                vertex_inlier_fast(Rf, tf, R, t, v[3], v[4], v[5], v[12], v[13], v[14], margin) &&
+                vertex_inlier_fast(Rf, tf, R, t, v[6], v[7], v[8], v[15], v[16], v[17], margin);
+      }
+      const int cnt = __popc(__ballot_sync(0xffffffffu, in0)) + __popc(__ballot_sync(0xffffffffu, in1));
+      if (lane == (h & 31)) { if (h < 32) acc0 += cnt; else acc1 += cnt; }
+      mk0 |= (unsigned long long)in0 << h;
+      mk1 |= (unsigned long long)in1 << h;
+    }
+    if (2 * c < kMaskCap && 2 * c < M) s_mask[2 * c] = mk0;
+    if (2 * c + 1 < kMaskCap && 2 * c + 1 < M) s_mask[2 * c + 1] = mk1;
   }
-  s_vote[tid] = (tid < H) ? vote : -1;
+  if (lane < H && acc0) atomicAdd(&s_vote[lane], acc0);
+  if (lane + 32 < H && acc1) atomicAdd(&s_vote[lane + 32], acc1);
   __syncthreads();
   if (tid == 0) {
     int best = 0, mv = 0;
@@ -1148,40 +1196,65 @@ __global__ void __launch_bounds__(kVerifyThreads) k_verify(VerifyParams P) {
   __syncthreads();
   const int best = s_best;
   if (best < 0) { if (tid == 0) { cd->score = -1; cd->best_hyp = -1; cd->ninlier = 0; } return; }
-  if (tid == best) {
+  double Rb[9], tb[3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) s_pose[i] = R[i];
+  for (int i = 0; i < 9; ++i) Rb[i] = s_pose[best][i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) s_pose[9 + i] = t[i];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = s_pose[i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) t[i] = s_pose[9 + i];
+  for (int i = 0; i < 3; ++i) tb[i] = s_pose[best][9 + i];
+  // ---- pass 2: inlier list of the best hypothesis, in match order.  Chunks of 64 tiles: the
+  // outcomes (mask bit, or a re-evaluation past kMaskCap) go to a per-thread bit mask with no
+  // barrier in between; one scan of the per-(tile, warp) counts gives every inlier its position.
+  constexpr int kWarps = kVerifyThreads / 32;
   int ninl = 0;
-  for (int jb = 0; jb < M; jb += kVerifyThreads) {
-    const int j = jb + tid;
-    bool ok = false;
-    if (j < M) {
-      float a[9], b[9];
-      load_pair(P, q0, moff + j, a, b);
-      ok = pair_inlier(R, t, a, b);
+  for (int cb = 0; cb < M; cb += 64 * kVerifyThreads) {
+    const int ntile = min(64, (M - cb + kVerifyThreads - 1) / kVerifyThreads);
+    unsigned long long okmask = 0ull;
+    for (int k = 0; k < ntile; ++k) {
+      const int j = cb + k * kVerifyThreads + tid;
+      bool ok = false;
+      if (j < M) {
+        if (j < kMaskCap) {
+          ok = (s_mask[j] >> best) & 1ull;
+        } else {
+          float a[9], b[9];
+          load_pair(P, q0, moff + j, a, b);
+          ok = pair_inlier(Rb, tb, a, b);
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (ok) okmask |= 1ull << k;
+      if (lane == 0) s_cnt[k * kWarps + wid] = __popc(bal);
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, ok);
     __syncthreads();
-    if ((tid & 31) == 0) s_wcnt[tid >> 5] = __popc(bal);
+    // exclusive scan of s_cnt[0 .. ntile*kWarps) by warp 0 (<= 256 entries: 8 per lane)
+    if (wid == 0) {
+      const int n = ntile * kWarps;
+      int v[2 * kWarps], sum = 0;
+#pragma unroll
+      for (int i = 0; i < 2 * kWarps; ++i) { const int e = lane * 2 * kWarps + i; v[i] = (e < n) ? s_cnt[e] : 0; sum += v[i]; }
+      int inc = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+      int run = inc - sum;
+#pragma unroll
+      for (int i = 0; i < 2 * kWarps; ++i) { const int e = lane * 2 * kWarps + i; if (e < n) s_cnt[e] = run; run += v[i]; }
+      if (lane == 31) s_cnt[64 * kWarps] = inc;
+    }
     __syncthreads();
-    const int before = ((tid >> 5) ? s_wcnt[0] : 0) + __popc(bal & ((1u << (tid & 31)) - 1u));
-    if (ok) P.inl[moff + ninl + before] = j;
-    ninl += s_wcnt[0] + s_wcnt[1];
+    for (int k = 0; k < ntile; ++k) {
+      const bool ok = (okmask >> k) & 1ull;
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (ok) P.inl[moff + ninl + s_cnt[k * kWarps + wid] + __popc(bal & ((1u << lane) - 1u))] = cb + k * kVerifyThreads + tid;
+    }
+    ninl += s_cnt[64 * kWarps];
+    __syncthreads();
   }
   if (tid == 0) {
     cd->score = ninl; cd->ninlier = ninl; cd->best_hyp = best;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) cd->R[i] = R[i];
+    for (int i = 0; i < 9; ++i) cd->R[i] = Rb[i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) cd->t[i] = t[i];
+    for (int i = 0; i < 3; ++i) cd->t[i] = tb[i];
   }
 }
 
