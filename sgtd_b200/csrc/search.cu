@@ -1078,12 +1078,13 @@ __device__ __forceinline__ f32x2 resid2_x2(const f32x2 *R2, const f32x2 *t2, f32
   return fma2(rx, rx, fma2(ry, ry, mul2(rz, rz)));
 }
 constexpr int kMaxHyp = 50;      // hypotheses per candidate (STDesc.cpp:486-489: skip_len = M / 50 + 1 => H <= 49)
-constexpr int kMaskCap = 2560;   // pairs whose outcome masks fit in shared memory; beyond it pass 2 re-evaluates
+constexpr int kBitWords = 2048;  // (hypothesis, warp tile) outcome words kept in shared memory; beyond it pass 2 re-evaluates
 
 __global__ void __launch_bounds__(kVerifyThreads, 5) k_verify(VerifyParams P) {
   __shared__ __align__(16) double s_pose[kMaxHyp][12];  // exact (R,t) of every hypothesis
   __shared__ __align__(16) float s_posef[kMaxHyp][16];  // rounded to float: R0..R8, t0..t2, margin(|t|), pad
-  __shared__ unsigned long long s_mask[kMaskCap];       // bit h of s_mask[j]: pair j is an inlier of hypothesis h
+  // s_bits[h * T + w]: ballots of hypothesis h over warp tile w (couples 32w..32w+31): .x pairs 2c, .y pairs 2c+1
+  __shared__ uint2 s_bits[kBitWords];
   __shared__ int s_vote[kMaxHyp];
   __shared__ int s_best, s_cnt[64 * (kVerifyThreads / 32) + 1];
   sgtd_candidate *cd = P.cands + blockIdx.x;
@@ -1113,9 +1114,14 @@ __global__ void __launch_bounds__(kVerifyThreads, 5) k_verify(VerifyParams P) {
   __syncthreads();
   // ---- pass 1: votes of every hypothesis
   const int ncouple = (M + 1) >> 1;
-  int acc0 = 0, acc1 = 0;  // lane l of a warp accumulates the warp's votes of hypotheses l and l+32
-  for (int c0 = wid * 32; c0 < ncouple; c0 += kVerifyThreads) {
-    const int c = c0 + lane;
+  const int T = (ncouple + 31) >> 5;        // warp tiles of the candidate
+  const bool keep = H * T <= kBitWords;     // every outcome bit fits in shared memory
+  const int Tc = keep ? T : kBitWords / H;  // warp tiles per chunk (a single chunk when everything fits)
+  for (int tb = 0; tb < T; tb += Tc) {
+  const int te = min(T, tb + Tc);
+  for (int w = tb + wid; w < te; w += kVerifyThreads / 32) {
+    const int c = w * 32 + lane;
+    uint2 *row = s_bits + (w - tb);
     // coordinate k of pairs 2c (.x) and 2c+1 (.y): a0..a8 = k 0..8, b0..b8 = k 9..17
     f32x2 K[18];
     float mgc = 0.f;
@@ -1140,7 +1146,6 @@ __global__ void __launch_bounds__(kVerifyThreads, 5) k_verify(VerifyParams P) {
       }
       mgc = fminf(fmaf(4.0e-5f, mx, 1.0e-4f), 8.0f);  // margin of the couple
     }
-    unsigned long long mk0 = 0ull, mk1 = 0ull;
     for (int h = 0; h < H; ++h) {
       const float4 p0 = *reinterpret_cast<const float4 *>(&s_posef[h][0]), p1 = *reinterpret_cast<const float4 *>(&s_posef[h][4]),
                    p2 = *reinterpret_cast<const float4 *>(&s_posef[h][8]);
@@ -1177,16 +1182,22 @@ __global__ void __launch_bounds__(kVerifyThreads, 5) k_verify(VerifyParams P) {
                 vertex_inlier_fast(Rf, tf, R, t, v[3], v[4], v[5], v[12], v[13], v[14], margin) &&
                 vertex_inlier_fast(Rf, tf, R, t, v[6], v[7], v[8], v[15], v[16], v[17], margin);
       }
-      const int cnt = __popc(__ballot_sync(0xffffffffu, in0)) + __popc(__ballot_sync(0xffffffffu, in1));
-      if (lane == (h & 31)) { if (h < 32) acc0 += cnt; else acc1 += cnt; }
-      mk0 |= (unsigned long long)in0 << h;
-      mk1 |= (unsigned long long)in1 << h;
+      const unsigned bal0 = __ballot_sync(0xffffffffu, in0), bal1 = __ballot_sync(0xffffffffu, in1);
+      if (lane == 0) *row = make_uint2(bal0, bal1);
+      row += Tc;
     }
-    if (2 * c < kMaskCap && 2 * c < M) s_mask[2 * c] = mk0;
-    if (2 * c + 1 < kMaskCap && 2 * c + 1 < M) s_mask[2 * c + 1] = mk1;
   }
-  if (lane < H && acc0) atomicAdd(&s_vote[lane], acc0);
-  if (lane + 32 < H && acc1) atomicAdd(&s_vote[lane + 32], acc1);
+  __syncthreads();
+  // votes of the chunk: population counts of the ballot words
+  const int nw = te - tb;
+  for (int idx = tid; idx < H * nw; idx += kVerifyThreads) {
+    const int hh = idx / nw;
+    const uint2 bw = s_bits[hh * Tc + (idx - hh * nw)];
+    const int n = __popc(bw.x) + __popc(bw.y);
+    if (n) atomicAdd(&s_vote[hh], n);
+  }
+  if (te < T) __syncthreads();  // the next chunk overwrites the words
+  }
   __syncthreads();
   if (tid == 0) {
     int best = 0, mv = 0;
@@ -1202,7 +1213,7 @@ __global__ void __launch_bounds__(kVerifyThreads, 5) k_verify(VerifyParams P) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) tb[i] = s_pose[best][9 + i];
   // ---- pass 2: inlier list of the best hypothesis, in match order.  Chunks of 64 tiles: the
-  // outcomes (mask bit, or a re-evaluation past kMaskCap) go to a per-thread bit mask with no
+  // outcomes (kept ballot bit, or a re-evaluation when they did not fit) go to a per-thread bit mask with no
   // barrier in between; one scan of the per-(tile, warp) counts gives every inlier its position.
   constexpr int kWarps = kVerifyThreads / 32;
   int ninl = 0;
@@ -1213,8 +1224,9 @@ __global__ void __launch_bounds__(kVerifyThreads, 5) k_verify(VerifyParams P) {
       const int j = cb + k * kVerifyThreads + tid;
       bool ok = false;
       if (j < M) {
-        if (j < kMaskCap) {
-          ok = (s_mask[j] >> best) & 1ull;
+        if (keep) {
+          const uint2 w = s_bits[best * T + (j >> 6)];
+          ok = (((j & 1) ? w.y : w.x) >> ((j >> 1) & 31)) & 1u;
         } else {
           float a[9], b[9];
           load_pair(P, q0, moff + j, a, b);

@@ -1,0 +1,3 @@
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/b.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_verify -s 3 -c 1 -o gpurun_out/prof_verify3 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/pv.log 2>&1
+grep -o '"result_crc": [0-9]*' gpurun_out/b.log; grep -o '"stage_ms": {[^}]*}' gpurun_out/b.log
