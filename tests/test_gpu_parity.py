@@ -199,6 +199,43 @@ def test_dense_scan_stress(oracle_lib):
         check_descs(gd[goff[s]:goff[s + 1]], o.build(xyz[s], labs[s]))
 
 
+def test_long_match_lists(oracle_lib):
+    """Candidates with thousands of match pairs: the verification kernel then scores the pairs in
+    several chunks and re-evaluates the winning hypothesis for the inlier list (search.cu, k_verify)."""
+    rng = np.random.default_rng(99)
+    K = 420
+    lm = np.column_stack([rng.uniform(-70, 70, (K, 2)), rng.uniform(-1, 4, K)])
+    lab = rng.integers(3, 6, K).astype(np.uint32)       # few classes -> many label-compatible triangles
+    mgr = capi.STDescManager(device=0)
+    o = oracle_lib.Oracle()
+    scans = [(lm + rng.normal(0, s, lm.shape)).astype(np.float32) for s in (0.0, 0.01, 0.02, 0.0)]
+    off = (np.arange(len(scans) + 1) * K).astype(np.int64)
+    b = mgr.build(capi.make_nodes(np.concatenate(scans), np.tile(lab, len(scans))), off,
+                  frame_ids=np.arange(len(scans), dtype=np.uint32))
+    for x in scans:
+        o.add(o.build(x, lab))
+    mgr.add(b)
+    q = (lm + rng.normal(0, 0.005, lm.shape)).astype(np.float32)
+    res = mgr.search(mgr.build(capi.make_nodes(q, lab)))
+    loops, cands = res.download()
+    r = o.search(o.build(q, lab))
+    n = r["n"]
+    oc = r["cands"]
+    assert n == len(scans) and loops["ncand"][0] == n
+    assert oc["nmatch"].max() > 6000, "the case must exceed the kernel's shared-memory outcome table"
+    for key in ("frame", "votes", "nmatch", "score", "best_hyp", "ninlier"):
+        assert (cands[key][0, :n] == oc[key]).all(), key
+    for c in range(n):
+        m_q, m_cell, m_g = res.matches(0, c, int(oc["nmatch"][c]))
+        sl = slice(oc["match_off"][c], oc["match_off"][c] + oc["nmatch"][c])
+        assert (m_q == r["m_q"][sl]).all() and (m_cell == r["m_cell"][sl]).all() and (m_g == r["m_g"][sl]).all()
+        inl = res.inliers(0, c, int(oc["ninlier"][c]))
+        assert (inl == r["inl"][oc["inlier_off"][c]: oc["inlier_off"][c] + oc["ninlier"][c]]).all()
+        assert np.abs(cands["t"][0, c] - oc["t"][c]).max() <= POSE_T_TOL
+        assert rot_angle_deg(cands["R"][0, c], oc["R"][c]) <= POSE_R_TOL_DEG
+    assert loops["frame"][0] == r["best"][0] and loops["score"][0] == r["best"][1]
+
+
 def test_db_snapshot_roundtrip(world, built, tmp_path):
     """sgtd_db_save / sgtd_db_load: a restored database answers queries identically."""
     mgr, o, *_ = built
