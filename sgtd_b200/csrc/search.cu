@@ -519,6 +519,19 @@ __global__ void k_set_offsets(sgtd_candidate *cands, const int64_t *cnt, const i
 
 // ============================ match lists ==========================================
 constexpr int kCollectThreads = 256;
+// ---- which candidates the inverted collect (k_collect_inv, below) takes
+constexpr int kSortCap = 4096;        // matches of a candidate
+constexpr int kInvMaxDesc = 8192;     // descriptors of its query (13 bits of the record)
+constexpr int kInvMaxEntries = 4096;  // entries of its keyframe (12 bits of the record)
+constexpr int kInvBinSort = 32;       // larger per-descriptor groups: the whole list is sorted instead
+constexpr unsigned long long kQtEmpty = 0xFFFFFFFFFFFFFFFFull;
+// A slot is (tag << 32) | (descriptor << 5 | ordinal): tag = high half of the key's hash (the low bits
+// give the position), so one 64-bit CAS inserts a probe and one 8-byte read tests it.  A tag hit is
+// confirmed against the key recomputed from the query descriptor, so the result stays exact.
+__device__ __forceinline__ bool inv_eligible(int nmatch, int64_t ndq, int nf) {
+  return nmatch <= kSortCap && ndq <= kInvMaxDesc && nf <= kInvMaxEntries;
+}
+
 constexpr int kSmemKeys = 4096;
 
 struct CollectParams {
@@ -528,7 +541,7 @@ struct CollectParams {
   const DescRec *db; const int64_t *frame_off; const uint64_t *f_key; const uint32_t *f_g;
   const double *f_side;  // side lengths in frame-view (key-sorted) order, 3 per entry
   int64_t frame_lo;
-  int skip_upto;         // candidates with nmatch <= skip_upto were handled by k_collect_inv
+  int skip_inv;          // 1: candidates that k_collect_inv handled (inv_eligible) are skipped
   uint32_t *m_q, *m_g; uint8_t *m_cell;
 };
 
@@ -603,12 +616,13 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
   __shared__ int s_yr[2];
   __shared__ uint32_t s_warp[kCollectThreads / 32];
   const sgtd_candidate c = P.cands[blockIdx.x];
-  if (c.match_off < 0 || c.nmatch <= P.skip_upto) return;
+  if (c.match_off < 0 || c.nmatch <= 0) return;
   const int q = blockIdx.x / P.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t fl = c.frame - P.frame_lo;
   const int64_t fo = P.frame_off[fl];
   const int nf = (int)(P.frame_off[fl + 1] - fo);
+  if (P.skip_inv && inv_eligible(c.nmatch, P.q_off[q + 1] - P.q_off[q], nf)) return;
   KeyFinder kf;
   kf.keys = P.f_key + fo; kf.nf = nf; kf.start = nullptr; kf.xmin = kf.xmax = kf.ymin = kf.ymax = 0; kf.ny = 1;
   if (nf > 0 && nf <= kSmemKeys) {
@@ -691,34 +705,36 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect(CollectParams P) {
 // k_collect walks ~14 probes for each of the query's ~2,000 descriptors (~30k lookups per candidate)
 // although a keyframe only has ~2,400 entries.  The inverted form builds, once per query, an
 // open-addressing multimap  probe key -> (descriptor << 5 | ordinal)  (k_query_index), and a candidate
-// CTA then looks its keyframe's ENTRIES up in it (12x fewer lookups); the matches come out in
-// keyframe order, so they are sorted in shared memory (bitonic, <= kSortCap records) on
-// (descriptor, ordinal, in-frame position) to restore the reference's order.  Candidates with more
-// matches than kSortCap are left to k_collect.
-constexpr int kSortCap = 4096;
-constexpr unsigned long long kQtEmpty = 0xFFFFFFFFFFFFFFFFull;
-struct __align__(16) QtSlot {  // one probe of a query: key and (descriptor << 5 | ordinal) in one 16-byte sector read
-  unsigned long long key;
-  uint32_t io, pad;
-};
-
-__global__ void __launch_bounds__(256) k_query_index(const DescRec *q, const QAux *aux, const int64_t *q_off, int q_base,
-                                                     QtSlot *qt, uint32_t ts) {
+// CTA then looks its keyframe's ENTRIES up in it (12x fewer lookups).  The matches come out in
+// keyframe order; a counting sort on the query descriptor (shared memory) plus a tiny per-descriptor
+// insertion sort on (ordinal, in-frame position) restores the reference's order.  Candidates that do
+// not fit the shared-memory tables (inv_eligible) are left to k_collect.
+constexpr int kIndexThreads = 1024;
+// One CTA per query: clears the query's table (it then sits in L2: 148 resident tables of ~0.6 MB) and
+// inserts every probe with one CAS.
+__global__ void __launch_bounds__(kIndexThreads) k_query_index(const DescRec *q, const QAux *aux, const int64_t *q_off,
+                                                               int q_base, unsigned long long *qt, uint32_t ts) {
   const int qi = q_base + blockIdx.x;  // tables are indexed by the query's position inside its group
   const int64_t q0 = q_off[qi], q1 = q_off[qi + 1];
-  QtSlot *tk = qt + (size_t)blockIdx.x * ts;
+  unsigned long long *tk = qt + (size_t)blockIdx.x * ts;
   const uint32_t mask = ts - 1;
-  for (int64_t d = q0 + threadIdx.x; d < q1; d += blockDim.x) {
+  {
+    const ulonglong2 e2 = make_ulonglong2(kQtEmpty, kQtEmpty);
+    ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(tk);
+    for (uint32_t i = threadIdx.x; i < ts / 2; i += kIndexThreads) t2[i] = e2;
+  }
+  __syncthreads();
+  for (int64_t d = q0 + threadIdx.x; d < q1; d += kIndexThreads) {
     const DescRec r = q[d];
     uint32_t m = aux[d].mask;
     const uint32_t il = (uint32_t)(d - q0);
     while (m) {
       const int ord = __ffs(m) - 1;
       m &= m - 1;
-      const unsigned long long key = probe_cell_key(r, ord);
-      uint32_t pos = (uint32_t)mix64(key) & mask;
-      while (atomicCAS(&tk[pos].key, kQtEmpty, key) != kQtEmpty) pos = (pos + 1) & mask;  // one slot per probe
-      tk[pos].io = (il << 5) | (uint32_t)ord;
+      const unsigned long long hsh = mix64(probe_cell_key(r, ord));
+      const unsigned long long val = (hsh & 0xFFFFFFFF00000000ull) | (unsigned long long)((il << 5) | (uint32_t)ord);
+      uint32_t pos = (uint32_t)hsh & mask;
+      while (atomicCAS(&tk[pos], kQtEmpty, val) != kQtEmpty) pos = (pos + 1) & mask;  // one slot per probe
     }
   }
 }
@@ -727,79 +743,148 @@ struct CollectInvParams {
   const sgtd_candidate *cands;
   int k;
   const DescRec *q; const QAux *aux; const int64_t *q_off;
-  const QtSlot *qt; uint32_t ts;
+  const unsigned long long *qt; uint32_t ts;
   int q_base;  // first query of the group the tables were built for
   const int64_t *frame_off; const uint64_t *f_key; const uint32_t *f_g; const double *f_side;
   int64_t frame_lo;
   uint32_t *m_q, *m_g; uint8_t *m_cell;
 };
+constexpr int kInvUnroll = 4;  // keyframe entries a thread looks up at a time (independent loads in flight)
 
+// dynamic shared memory: records [kSortCap] u32, sorted records [kSortCap] u32, per-descriptor
+// counters / offsets [bins] u16 (updated two per 32-bit atomic)
 __global__ void __launch_bounds__(kCollectThreads) k_collect_inv(CollectInvParams P) {
-  __shared__ unsigned long long s_key[kSortCap];
-  __shared__ uint32_t s_n;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  uint32_t *s_rec = reinterpret_cast<uint32_t *>(s_dyn);
+  uint32_t *s_out = s_rec + kSortCap;
+  uint32_t *s_bin32 = s_out + kSortCap;
+  uint16_t *s_bin16 = reinterpret_cast<uint16_t *>(s_bin32);
+  __shared__ uint32_t s_n, s_big, s_wsum[kCollectThreads / 32];
   const size_t cslot = (size_t)P.q_base * P.k + blockIdx.x;
   const sgtd_candidate c = P.cands[cslot];
-  if (c.match_off < 0 || c.nmatch <= 0 || c.nmatch > kSortCap) return;
+  if (c.match_off < 0 || c.nmatch <= 0) return;
   const int q = (int)(cslot / P.k);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t fl = c.frame - P.frame_lo;
   const int64_t fo = P.frame_off[fl];
   const int nf = (int)(P.frame_off[fl + 1] - fo);
   const int64_t q0 = P.q_off[q];
-  const QtSlot *tk = P.qt + (size_t)(q - P.q_base) * P.ts;
+  const int ndq = (int)(P.q_off[q + 1] - q0);
+  if (!inv_eligible(c.nmatch, ndq, nf)) return;
+  const unsigned long long *tk = P.qt + (size_t)(q - P.q_base) * P.ts;
   const uint32_t mask = P.ts - 1;
-  int npad = 1;
-  while (npad < c.nmatch) npad <<= 1;
-  if (tid == 0) s_n = 0;
-  for (int i = tid; i < npad; i += kCollectThreads) s_key[i] = kQtEmpty;  // padding sorts last
+  if (tid == 0) { s_n = 0; s_big = 0; }
+  for (int i = tid; i < (ndq + 1) / 2; i += kCollectThreads) s_bin32[i] = 0;
   __syncthreads();
-  for (int p = tid; p < nf; p += kCollectThreads) {
-    const unsigned long long key = P.f_key[fo + p];
-    uint32_t pos = (uint32_t)mix64(key) & mask;
-    bool have = false;
-    double e0 = 0, e1 = 0, e2 = 0;
-    while (true) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(tk + pos));
-      const unsigned long long kk = ((unsigned long long)raw.y << 32) | raw.x;
-      if (kk == kQtEmpty) break;
-      if (kk == key) {
-        if (!have) { e0 = P.f_side[3 * (fo + p)]; e1 = P.f_side[3 * (fo + p) + 1]; e2 = P.f_side[3 * (fo + p) + 2]; have = true; }
-        const uint32_t io = raw.z;
-        const DescRec r = P.q[q0 + (io >> 5)];
-        if (r.frame != (uint32_t)c.frame) {
-          const double d2 = sqn3(__dsub_rn(r.s[0], e0), __dsub_rn(r.s[1], e1), __dsub_rn(r.s[2], e2));
-          if (d2 < P.aux[q0 + (io >> 5)].thr2) {
-            const uint32_t slot = atomicAdd(&s_n, 1u);
-            if (slot < (uint32_t)kSortCap) {
-              // sort key: descriptor (26 bits) | ordinal (5) | position in the key-sorted view (24) -- equal
-              // keys keep in-frame order in the view, so position order == the reference's bucket order j
-              s_key[slot] = ((unsigned long long)(io >> 5) << 32) | ((unsigned long long)(io & 31u) << 24) | (unsigned long long)p;
+  // ---- lookups: record = descriptor (13 bits) | ordinal (5) | position in the key-sorted view (12);
+  // equal keys keep in-frame order in the view, so position order == the reference's bucket order j
+  for (int pb = 0; pb < nf; pb += kInvUnroll * kCollectThreads) {
+    unsigned long long key[kInvUnroll], slot[kInvUnroll];
+    uint32_t pos[kInvUnroll];
+#pragma unroll
+    for (int u = 0; u < kInvUnroll; ++u) {
+      const int p = pb + u * kCollectThreads + tid;
+      key[u] = (p < nf) ? P.f_key[fo + p] : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < kInvUnroll; ++u) {
+      const int p = pb + u * kCollectThreads + tid;
+      const unsigned long long hsh = mix64(key[u]);
+      pos[u] = (uint32_t)hsh & mask;
+      slot[u] = (p < nf) ? __ldg(tk + pos[u]) : kQtEmpty;
+    }
+#pragma unroll
+    for (int u = 0; u < kInvUnroll; ++u) {
+      const int p = pb + u * kCollectThreads + tid;
+      if (slot[u] == kQtEmpty) continue;
+      const uint32_t tag = (uint32_t)(mix64(key[u]) >> 32);
+      bool have = false;
+      double e0 = 0, e1 = 0, e2 = 0;
+      unsigned long long sl = slot[u];
+      uint32_t ps = pos[u];
+      while (sl != kQtEmpty) {
+        if ((uint32_t)(sl >> 32) == tag) {
+          const uint32_t io = (uint32_t)sl;
+          const DescRec r = P.q[q0 + (io >> 5)];
+          if (probe_cell_key(r, (int)(io & 31u)) == key[u] && r.frame != (uint32_t)c.frame) {
+            if (!have) { e0 = P.f_side[3 * (fo + p)]; e1 = P.f_side[3 * (fo + p) + 1]; e2 = P.f_side[3 * (fo + p) + 2]; have = true; }
+            const double d2 = sqn3(__dsub_rn(r.s[0], e0), __dsub_rn(r.s[1], e1), __dsub_rn(r.s[2], e2));
+            if (d2 < P.aux[q0 + (io >> 5)].thr2) {
+              const uint32_t at = atomicAdd(&s_n, 1u);
+              if (at < (uint32_t)kSortCap) {
+                const uint32_t i = io >> 5;
+                s_rec[at] = (i << 17) | ((io & 31u) << 12) | (uint32_t)p;
+                atomicAdd(&s_bin32[i >> 1], 1u << (16 * (i & 1u)));
+              }
             }
           }
         }
+        ps = (ps + 1) & mask;
+        sl = __ldg(tk + ps);
       }
-      pos = (pos + 1) & mask;
     }
   }
   __syncthreads();
-  // bitonic sort of npad (key, value) pairs in shared memory
-  for (int size = 2; size <= npad; size <<= 1)
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < npad / 2; i += kCollectThreads) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const unsigned long long a = s_key[lo], b = s_key[hi];
-        if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
-      }
-      __syncthreads();
-    }
   const int n = (int)min(s_n, (uint32_t)c.nmatch);
+  // ---- counting sort on the descriptor: exclusive scan of the counters ...
+  {
+    const int per = (ndq + kCollectThreads - 1) / kCollectThreads;
+    const int b0 = min(ndq, tid * per), b1 = min(ndq, b0 + per);
+    uint32_t sum = 0;
+    for (int b = b0; b < b1; ++b) sum += s_bin16[b];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) s_wsum[wid] = inc;
+    __syncthreads();
+    uint32_t run = inc - sum;
+    for (int w = 0; w < wid; ++w) run += s_wsum[w];
+    for (int b = b0; b < b1; ++b) { const uint32_t cnt = s_bin16[b]; s_bin16[b] = (uint16_t)run; run += cnt; }
+  }
+  __syncthreads();
+  // ... scatter (a counter ends as the END of its group) ...
+  for (int r = tid; r < n; r += kCollectThreads) {
+    const uint32_t rec = s_rec[r], i = rec >> 17, sh = 16 * (i & 1u);
+    const uint32_t old = atomicAdd(&s_bin32[i >> 1], 1u << sh);
+    s_out[(old >> sh) & 0xFFFFu] = rec;
+  }
+  __syncthreads();
+  // ... and order inside each descriptor's group (usually 0-2 records) by (ordinal, position)
+  for (int i = tid; i < ndq; i += kCollectThreads) {
+    const int b = i ? s_bin16[i - 1] : 0, e = s_bin16[i];
+    if (e - b < 2) continue;
+    if (e - b > kInvBinSort) { s_big = 1; continue; }
+    for (int x = b + 1; x < e; ++x) {
+      const uint32_t v = s_out[x];
+      int y = x - 1;
+      while (y >= b && s_out[y] > v) { s_out[y + 1] = s_out[y]; --y; }
+      s_out[y + 1] = v;
+    }
+  }
+  __syncthreads();
+  if (s_big) {
+    // degenerate geometry (one descriptor matching a large part of the keyframe): bitonic sort of everything
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    for (int i = n + tid; i < npad; i += kCollectThreads) s_out[i] = 0xFFFFFFFFu;  // padding sorts last
+    __syncthreads();
+    for (int size = 2; size <= npad; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < npad / 2; i += kCollectThreads) {
+          const int lo = 2 * i - (i & (stride - 1));
+          const int hi = lo + stride;
+          const bool up = (lo & size) == 0;
+          const uint32_t a = s_out[lo], b = s_out[hi];
+          if ((a > b) == up) { s_out[lo] = b; s_out[hi] = a; }
+        }
+        __syncthreads();
+      }
+  }
   for (int i = tid; i < n; i += kCollectThreads) {
-    const unsigned long long kk = s_key[i];
-    P.m_q[c.match_off + i] = (uint32_t)(kk >> 32);
-    P.m_cell[c.match_off + i] = (uint8_t)((kk >> 24) & 31u);
-    P.m_g[c.match_off + i] = P.f_g[fo + (int64_t)(kk & 0xFFFFFFull)];
+    const uint32_t rec = s_out[i];
+    P.m_q[c.match_off + i] = rec >> 17;
+    P.m_cell[c.match_off + i] = (uint8_t)((rec >> 12) & 31u);
+    P.m_g[c.match_off + i] = P.f_g[fo + (int64_t)(rec & 0xFFFu)];
   }
 }
 
@@ -1369,7 +1454,7 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   // all queries of the batch in one group: splitting the batch so that the tables stay L2-resident was
   // measured slower (too little parallelism per launch); SGTD_COLLECT_GROUP overrides for experiments
   const int qt_group = getenv("SGTD_COLLECT_GROUP") ? std::max(1, atoi(getenv("SGTD_COLLECT_GROUP"))) : std::max(nq, 1);
-  size_t o_qtk = o; o += al((size_t)qt_group * qt_ts * 16);
+  size_t o_qtk = o; o += al((size_t)qt_group * qt_ts * 8);
   size_t o_jc = o; o += al(64);
   size_t o_jcub = o; o += al(cubj);
   SGTD_CUDA(h, h->scratch.reserve(o, st, false));
@@ -1501,16 +1586,19 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
       // per-query probe multimap, then one lookup per keyframe entry + shared-memory sort
       CollectInvParams I{};
       I.cands = r->cands.p; I.k = k; I.q = qb->rec.p; I.aux = aux; I.q_off = qb->d_off.p;
-      I.qt = (const QtSlot *)(S + o_qtk); I.ts = qt_ts;
+      I.qt = (const unsigned long long *)(S + o_qtk); I.ts = qt_ts;
       I.frame_off = h->d_frame_off.p; I.f_key = h->f_key.p; I.f_g = h->f_g.p; I.f_side = h->f_side.p;
       I.frame_lo = h->frame_lo();
       I.m_q = r->m_q.p; I.m_g = r->m_g.p; I.m_cell = r->m_cell.p;
+      // shared memory of a candidate CTA: two record arrays + one 16-bit counter per query descriptor
+      const size_t inv_smem = 2 * (size_t)kSortCap * 4 + 4 * (size_t)((std::min<int64_t>(max_dq, kInvMaxDesc) + 1) / 2);
+      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        2 * kSortCap * 4 + 2 * kInvMaxDesc));
       for (int qb0 = 0; qb0 < nq; qb0 += qt_group) {
         const int gq = std::min(qt_group, nq - qb0);
-        SGTD_CUDA(h, cudaMemsetAsync(S + o_qtk, 0xFF, (size_t)gq * qt_ts * sizeof(QtSlot), st));
-        k_query_index<<<gq, 256, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (QtSlot *)(S + o_qtk), qt_ts);
+        k_query_index<<<gq, kIndexThreads, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (unsigned long long *)(S + o_qtk), qt_ts);
         I.q_base = qb0;
-        k_collect_inv<<<(unsigned)gq * k, kCollectThreads, 0, st>>>(I);
+        k_collect_inv<<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
         h->launches += 2;
       }
     }
@@ -1518,7 +1606,7 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
     C.cands = r->cands.p; C.k = k; C.q = qb->rec.p; C.aux = aux; C.q_off = qb->d_off.p;
     C.db = h->rec.p; C.frame_off = h->d_frame_off.p; C.f_key = h->f_key.p; C.f_g = h->f_g.p;
     C.f_side = h->f_side.p; C.frame_lo = h->frame_lo();
-    C.skip_upto = inverted ? kSortCap : 0;
+    C.skip_inv = inverted ? 1 : 0;
     C.m_q = r->m_q.p; C.m_g = r->m_g.p; C.m_cell = r->m_cell.p;
     k_collect<<<(unsigned)nslot, kCollectThreads, 0, st>>>(C);
     SGTD_LAUNCHED(h);
