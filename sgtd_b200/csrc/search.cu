@@ -173,6 +173,38 @@ __global__ void __launch_bounds__(kVoteThreads) k_vote(VoteParams P) {
   if (lane == 0 && P.counters) atomicAdd(P.counters + 4, cM);
 }
 
+// ============================ packed FP32 ===========================================
+// Blackwell's packed FP32 (FFMA2/FADD2/FMUL2: two IEEE single operations per instruction) halves
+// the issue slots of the FP32 pre-filters of k_vote_join and k_verify.  The packed operands are kept
+// as 64-bit registers (inline PTX) so that loop-invariant pairs stay in aligned register pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // ============================ vote as a bucket-major join ===========================
 // The per-probe formulation above re-reads every bucket once per probe (a 1,024-query
 // batch probes the average bucket ~20 times).  The join inverts the loop nest:
@@ -241,7 +273,7 @@ struct JoinParams {
   const Bucket *table;
   const double *s0, *s1, *s2; const uint32_t *fr;
   const float4 *pack;  // {float s0, s1, s2, frame bits} per entry, key-major
-  double band;         // relative half-width of the FP32 decision band
+  double band;         // half-width of the FP32 decision band, relative to thr^2
   uint32_t frame_lo; int64_t F;
   uint32_t *votes;
   unsigned long long *seg_counter, *counters;
@@ -249,12 +281,13 @@ struct JoinParams {
 };
 
 // FP32 pre-filter of the rough distance test.  DB sides are also kept as float (16-byte packed entry
-// {s0, s1, s2, frame}); the squared distance is first formed in float.  With u = 2^-24, sides <= S'
-// and ||d|| ~ thr at the decision boundary, |d2_f - d2| <= (6.93 u S'/thr + 5 u) thr^2, and
-// S'/thr <= (1 + rough)/rough, so outside the relative band  thr^2 (1 -+ m),
-// m = 2e-6 (1 + 1/rough)  (>= 4x the bound), the float decision equals the reference's FP64 one;
-// inside the band (a ~1e-4 fraction of boundary cases) the entry's FP64 sides are loaded and the
-// exact expression is evaluated.  Halves the bytes per entry and moves the test to the FP32 pipe.
+// {s0, s1, s2, frame}); s = ||q - e||^2 - thr^2 is first formed in float (packed FP32, two entries per
+// instruction, the accumulation starting at -thr^2).  With u = 2^-24, sides <= S' and ||d|| ~ thr at the
+// decision boundary, the float value is off by at most (6.93 u S'/thr + 8 u) thr^2, and
+// S'/thr <= (1 + rough)/rough, so outside the band |s| <= w,  w = 1.25 * 2e-6 (1 + 1/rough) thr^2
+// (>= 4x the bound), the sign of s decides exactly like the reference's FP64 test; inside the band
+// (a ~1e-4 fraction of boundary cases) the entry's FP64 sides are loaded and the exact expression is
+// evaluated.  Halves the bytes per entry and moves the test to the FP32 pipe.
 // Exact (reference) evaluation of the entries a lane found inside the FP32 decision band.
 template <bool kDoVote>
 __device__ __noinline__ uint32_t join_exact(const JoinParams &P, const double *qs, uint32_t *row, uint32_t o, uint32_t n,
@@ -274,14 +307,22 @@ __device__ __noinline__ uint32_t join_exact(const JoinParams &P, const double *q
   return hits;
 }
 
+// votes[...] += 1 where `hit`: one predicated RED instead of a branch around it
+__device__ __forceinline__ void red_inc_if(uint32_t *addr, bool hit) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0;\n @p red.global.add.u32 [%0], 1;\n}" ::"l"(addr), "r"((uint32_t)hit)
+               : "memory");
+}
+
+static_assert(kVoteUnroll == 4, "k_vote_join pairs the entries of a trip as (0,1) and (2,3)");
 template <bool kDoVote>
 __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
-  __shared__ double sh_s[kVoteThreads / 32][kJoinSeg][4];    // s0, s1, s2, thr2 of each probe of the segment (exact path)
-  __shared__ float sh_f[kVoteThreads / 32][kJoinSeg][6];     // float s0, s1, s2, lo, hi of the band
-  __shared__ uint32_t sh_q[kVoteThreads / 32][kJoinSeg][2];  // query index, query frame id
+  __shared__ double sh_s[kVoteThreads / 32][kJoinSeg][4];  // s0, s1, s2, thr2 of each probe of the segment (exact path)
+  __shared__ float4 sh_f[kVoteThreads / 32][kJoinSeg];     // float s0, s1, s2, -thr2
+  __shared__ uint4 sh_g[kVoteThreads / 32][kJoinSeg];      // band half-width w (float bits), query frame id, vote row pointer
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned long long nseg = (P.npairs + kJoinSeg - 1) / kJoinSeg;
-  uint32_t cM = 0;  // per-thread match count (< 2^32: a thread sees a 1/150k share of the batch)
+  const f32x2 negzero2 = pack2(-0.f, -0.f);
+  uint32_t cM = 0;  // matches seen by this thread (only counted here when no votes are cast; else k_topk sums the rows)
   while (true) {
     unsigned long long seg = 0;
     if (lane == 0) seg = atomicAdd(P.seg_counter, 1ull);
@@ -297,10 +338,11 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
       const DescRec r = P.q[d];
       const QAux a = P.aux[d];
       sh_s[wid][lane][0] = r.s[0]; sh_s[wid][lane][1] = r.s[1]; sh_s[wid][lane][2] = r.s[2]; sh_s[wid][lane][3] = a.thr2;
-      sh_f[wid][lane][0] = (float)r.s[0]; sh_f[wid][lane][1] = (float)r.s[1]; sh_f[wid][lane][2] = (float)r.s[2];
-      sh_f[wid][lane][3] = __double2float_rd(a.thr2 * (1.0 - P.band));  // below: certainly a match
-      sh_f[wid][lane][4] = __double2float_ru(a.thr2 * (1.0 + P.band));  // above: certainly not
-      sh_q[wid][lane][0] = a.qi; sh_q[wid][lane][1] = r.frame - P.frame_lo;
+      sh_f[wid][lane] = make_float4((float)r.s[0], (float)r.s[1], (float)r.s[2], -(float)a.thr2);
+      const unsigned long long rowp = (unsigned long long)(P.votes + (size_t)a.qi * (size_t)P.F);
+      // query frame id relative to this shard; (src.frame_id_ - db.frame_id_) > 0 on unsigned == "!=" (STDesc.cpp:373)
+      sh_g[wid][lane] = make_uint4(__float_as_uint(__double2float_ru(a.thr2 * P.band)), r.frame - P.frame_lo,
+                                   (uint32_t)rowp, (uint32_t)(rowp >> 32));
     }
     __syncwarp();
     int i = 0;
@@ -317,37 +359,58 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
           // streaming loads (ld.global.cs, evict-first): bucket tiles must not push the vote rows that the
           // RED.ADDs below keep hitting out of L2
           v[u] = __ldcs(P.pack + (size_t)o + (e < n ? e : n - 1));
-          // tail lanes re-read the last entry: give them a frame id no query can have so they never count
-          if (e >= n) v[u].w = __uint_as_float(0xFFFFFFFFu);
+          // tail lanes re-read the last entry: put it at infinity so that it is neither a match nor ambiguous
+          if (e >= n) v[u].x = __int_as_float(0x7f800000);
         }
+        // entries (0,1) and (2,3) side by side; "+ (-0)" (the identity) makes each pair the result of a
+        // packed instruction, i.e. pins it in an aligned register pair for the whole run
+        f32x2 X[2], Y[2], Z[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          X[j] = add2(pack2(v[2 * j].x, v[2 * j + 1].x), negzero2);
+          Y[j] = add2(pack2(v[2 * j].y, v[2 * j + 1].y), negzero2);
+          Z[j] = add2(pack2(v[2 * j].z, v[2 * j + 1].z), negzero2);
+        }
+        uint32_t fr[kVoteUnroll];
+#pragma unroll
+        for (int u = 0; u < kVoteUnroll; ++u) fr[u] = __float_as_uint(v[u].w);
         for (int p = i; p < i + run; ++p) {
-          const float q0 = sh_f[wid][p][0], q1 = sh_f[wid][p][1], q2 = sh_f[wid][p][2];
-          const float lo = sh_f[wid][p][3], hi = sh_f[wid][p][4];
-          const uint32_t qfl = sh_q[wid][p][1];  // query frame id relative to this shard (never 0xFFFFFFFF)
-          uint32_t *row = P.votes + (size_t)sh_q[wid][p][0] * (size_t)P.F;
-          uint32_t amb = 0;
+          const float4 qf = sh_f[wid][p];
+          const uint4 g = sh_g[wid][p];
+          const float wb = __uint_as_float(g.x);
+          uint32_t *row = reinterpret_cast<uint32_t *>(((unsigned long long)g.w << 32) | g.z);
+          const f32x2 Q0 = pack2(qf.x, qf.x), Q1 = pack2(qf.y, qf.y), Q2 = pack2(qf.z, qf.z), NT = pack2(qf.w, qf.w);
+          float sd[kVoteUnroll];  // ||q - e||^2 - thr^2
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const f32x2 dx = sub2(Q0, X[j]), dy = sub2(Q1, Y[j]), dz = sub2(Q2, Z[j]);
+            unpack2(fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, NT))), sd[2 * j], sd[2 * j + 1]);
+          }
 #pragma unroll
           for (int u = 0; u < kVoteUnroll; ++u) {
-            const uint32_t f = __float_as_uint(v[u].w);
-            const float dx = q0 - v[u].x, dy = q1 - v[u].y, dz = q2 - v[u].z;
-            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-            // (src.frame_id_ - db.frame_id_) > 0 on unsigned == "!=" (STDesc.cpp:373)
-            const bool live = (f != qfl) && (f != 0xFFFFFFFFu);
-            const bool hit = live && d2 < lo;
-            if (live && d2 >= lo && d2 <= hi) amb |= 1u << u;  // inside the decision band
-            if (kDoVote && hit) atomicAdd(row + f, 1u);
-            cM += hit;
+            const bool hit = (fr[u] != g.y) && sd[u] < -wb;  // certainly a match
+            if (kDoVote) red_inc_if(row + fr[u], hit);
+            else cM += hit;
           }
-          if (amb) cM += join_exact<kDoVote>(P, sh_s[wid][p], row, o, n, e0 + lane, amb);  // rare
+          const float nearest = fminf(fminf(fabsf(sd[0]), fabsf(sd[1])), fminf(fabsf(sd[2]), fabsf(sd[3])));
+          if (nearest <= wb) {  // rare: some entry is inside the decision band
+            uint32_t amb = 0;
+#pragma unroll
+            for (int u = 0; u < kVoteUnroll; ++u)
+              if ((fr[u] != g.y) && fabsf(sd[u]) <= wb) amb |= 1u << u;
+            if (amb) cM += join_exact<kDoVote>(P, sh_s[wid][p], row, o, n, e0 + lane, amb);
+          }
         }
       }
       i += run;
     }
   }
-  unsigned long long cM64 = cM;
+  if (!kDoVote) {
+    unsigned long long cM64 = cM;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cM64 += __shfl_xor_sync(0xffffffffu, cM64, o);
-  if (lane == 0 && cM64) atomicAdd(P.counters + 4, cM64);
+    for (int o = 16; o > 0; o >>= 1) cM64 += __shfl_xor_sync(0xffffffffu, cM64, o);
+    if (lane == 0 && cM64) atomicAdd(P.counters + 4, cM64);
+  }
 }
 
 // ============================ top-k ==============================================
@@ -377,8 +440,11 @@ __device__ __forceinline__ T block_sum(T v, T *s_tmp) {
 // frame asc) among those with >= 5 votes.  Radix-select on the 32-bit vote
 // value (3 histogram passes over the row) finds the k-th largest value T; all
 // rows > T are taken, ties at T are taken in ascending frame order.
+// m_counter (optional): += the sum of the row, i.e. the number of matches of the query (the join casts
+// its votes with predicated REDs and leaves the counting to this pass, which reads every row anyway)
 __global__ void __launch_bounds__(kTopkThreads) k_topk(const uint32_t *votes, int64_t F, uint32_t frame_lo, int k,
-                                                       int32_t *out_votes, int32_t *out_frames) {
+                                                       int32_t *out_votes, int32_t *out_frames,
+                                                       unsigned long long *m_counter) {
   __shared__ uint32_t s_hist[2048];
   __shared__ unsigned long long s_list[kMaxCand];
   __shared__ uint32_t s_scan[kTopkThreads];
@@ -389,8 +455,14 @@ __global__ void __launch_bounds__(kTopkThreads) k_topk(const uint32_t *votes, in
   const uint32_t *row = votes + (size_t)q * (size_t)F;
   // pass A: how many keyframes have >= 5 votes
   uint32_t n5 = 0;
-  for (int64_t f = tid; f < F; f += kTopkThreads) n5 += row[f] >= 5u;
+  unsigned long long msum = 0;
+  for (int64_t f = tid; f < F; f += kTopkThreads) { const uint32_t v = row[f]; n5 += v >= 5u; msum += v; }
   n5 = block_sum<uint32_t>(n5, s_tmp);
+  if (m_counter) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+    if ((tid & 31) == 0 && msum) atomicAdd(m_counter, msum);
+  }
   uint32_t T, r;  // take v > T, plus the first r (frame asc) with v == T
   if (n5 <= (uint32_t)k) { T = 4; r = 0; }
   else {
@@ -1124,37 +1196,7 @@ __device__ __forceinline__ bool vertex_inlier_fast(const float *Rf, const float 
   return sqn3(dx, dy, dz) < 9.0;
 }
 
-// Two pairs per instruction: Blackwell's packed FP32 (FFMA2/FADD2/FMUL2) halves the issue
-// slots of the pre-filter.  Each half is an IEEE fmaf, so the values equal resid2_f32()'s.
-// The packed operands are kept as 64-bit registers (inline PTX) so that the pair coordinates
-// stay in aligned register pairs across the hypothesis loop instead of being re-packed.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
+// |R p + t - b|^2 of two pairs at once; each half is an IEEE fmaf chain, so the values equal resid2_f32()'s
 __device__ __forceinline__ f32x2 resid2_x2(const f32x2 *R2, const f32x2 *t2, f32x2 px, f32x2 py, f32x2 pz, f32x2 bx,
                                            f32x2 by, f32x2 bz) {
   const f32x2 rx = sub2(fma2(R2[0], px, fma2(R2[1], py, fma2(R2[2], pz, t2[0]))), bx);
@@ -1428,6 +1470,7 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   size_t o_aux = o; o += al((size_t)std::max<int64_t>(qb->n, 1) * sizeof(QAux));
   // vote formulation: bucket-major join (default) or per-probe streaming (SGTD_VOTE_MODE=stream)
   const char *vmode = getenv("SGTD_VOTE_MODE");
+  bool m_by_topk = false;  // the join leaves the match count (stats) to k_topk
   const bool join_mode = !(vmode && strcmp(vmode, "stream") == 0) && qb->n > 0 && h->rec.n > 0;
   bool join_timed = false;
   const bool sort_q = !join_mode && qb->n > 0;  // streaming mode walks descriptors in cell-key order (L2 reuse)
@@ -1526,13 +1569,13 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
         J.pkey = (uint32_t *)(S + o_jk1); J.pval = (uint32_t *)(S + o_jv1); J.npairs = npairs;
         J.q = qb->rec.p; J.aux = aux; J.table = h->table.p;
         J.s0 = h->v_s0.p; J.s1 = h->v_s1.p; J.s2 = h->v_s2.p; J.fr = h->v_frame.p;
-        J.pack = h->v_pack.p; J.band = 2.0e-6 * (1.0 + 1.0 / h->c.rough);
+        J.pack = h->v_pack.p; J.band = 2.5e-6 * (1.0 + 1.0 / h->c.rough);
         J.frame_lo = (uint32_t)h->frame_lo(); J.F = Fa; J.votes = r->votes.p;
         J.seg_counter = d_cursor + 1; J.counters = r->counters.p; J.slot_mask = (uint32_t)((1ull << sbits) - 1);
         SGTD_CUDA(h, cudaEventRecord(ev[8], st));
         const int jgrid = h->sm_count * 4;
         if (getenv("SGTD_DEBUG_NOVOTE")) k_vote_join<false><<<jgrid, kVoteThreads, 0, st>>>(J);
-        else k_vote_join<true><<<jgrid, kVoteThreads, 0, st>>>(J);
+        else { k_vote_join<true><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
         SGTD_LAUNCHED(h);
         SGTD_CUDA(h, cudaGetLastError());
         join_timed = true;
@@ -1542,7 +1585,8 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   SGTD_CUDA(h, cudaEventRecord(ev[1], st));
   const int vote_launches = (int)(h->launches - launches0);
   if (nq > 0) {
-    k_topk<<<nq, kTopkThreads, 0, st>>>(r->votes.p, Fa, (uint32_t)h->frame_lo(), k, lv, lf);
+    k_topk<<<nq, kTopkThreads, 0, st>>>(r->votes.p, Fa, (uint32_t)h->frame_lo(), k, lv, lf,
+                                        m_by_topk ? r->counters.p + 4 : nullptr);
     SGTD_LAUNCHED(h);
     SGTD_CUDA(h, cudaGetLastError());
   }
