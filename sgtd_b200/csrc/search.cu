@@ -1147,6 +1147,7 @@ struct VerifyParams {
   const DescVert *dbv;
   const uint32_t *m_q, *m_g;
   int32_t *inl;
+  double *pose;  // kMaxHyp x 12 doubles per candidate: (R row-major, t) of every hypothesis
 };
 
 __device__ __forceinline__ void load_pair(const VerifyParams &P, int64_t q0, int64_t j, float *a, float *b) {
@@ -1207,6 +1208,30 @@ __device__ __forceinline__ f32x2 resid2_x2(const f32x2 *R2, const f32x2 *t2, f32
 constexpr int kMaxHyp = 50;      // hypotheses per candidate (STDesc.cpp:486-489: skip_len = M / 50 + 1 => H <= 49)
 constexpr int kBitWords = 2048;  // (hypothesis, warp tile) outcome words kept in shared memory; beyond it pass 2 re-evaluates
 
+// One thread per (candidate, hypothesis): the 3-point Kabsch of match pair h * skip
+// (triangle_solver, STDesc.cpp:574-622), all in FP64.  Kept out of k_verify: its long dependent
+// FP64 chains would otherwise hold the scoring warps of a CTA at a barrier.
+__global__ void __launch_bounds__(128) k_hypotheses(VerifyParams P, int nslot) {
+  const int gid = blockIdx.x * 128 + threadIdx.x;
+  const int cslot = gid / kMaxHyp, hh = gid - cslot * kMaxHyp;
+  if (cslot >= nslot) return;
+  const sgtd_candidate *cd = P.cands + cslot;
+  const int64_t moff = cd->match_off;
+  const int M = cd->nmatch;
+  if (moff < 0 || M <= 0) return;
+  const int skip = M / 50 + 1;
+  if (hh >= M / skip) return;
+  float a[9], b[9];
+  double R[9], t[3];
+  load_pair(P, P.q_off[cslot / P.k], moff + (int64_t)hh * skip, a, b);
+  kabsch3(a, b, R, t);
+  double *o = P.pose + ((size_t)cslot * kMaxHyp + hh) * 12;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) o[i] = R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[9 + i] = t[i];
+}
+
 __global__ void __launch_bounds__(kVerifyThreads, 5) k_verify(VerifyParams P) {
   __shared__ __align__(16) double s_pose[kMaxHyp][12];  // exact (R,t) of every hypothesis
   __shared__ __align__(16) float s_posef[kMaxHyp][16];  // rounded to float: R0..R8, t0..t2, margin(|t|), pad
@@ -1223,18 +1248,17 @@ __global__ void __launch_bounds__(kVerifyThreads, 5) k_verify(VerifyParams P) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int skip = M / 50 + 1;
   const int H = M / skip;
-  if (tid < H) {
-    float a[9], b[9];
-    double R[9], t[3];
-    load_pair(P, q0, moff + (int64_t)tid * skip, a, b);
-    kabsch3(a, b, R, t);
-    float tmax = 0.f;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { s_pose[tid][i] = R[i]; s_posef[tid][i] = (float)R[i]; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      s_pose[tid][9 + i] = t[i]; s_posef[tid][9 + i] = (float)t[i]; tmax = fmaxf(tmax, fabsf((float)t[i]));
+  {
+    const double *src = P.pose + (size_t)blockIdx.x * kMaxHyp * 12;
+    for (int i = tid; i < H * 12; i += kVerifyThreads) {
+      const double v = src[i];
+      const int hh = i / 12, e = i - hh * 12;
+      s_pose[hh][e] = v; s_posef[hh][e] = (float)v;
     }
+  }
+  __syncthreads();
+  if (tid < H) {
+    const float tmax = fmaxf(fabsf(s_posef[tid][9]), fmaxf(fabsf(s_posef[tid][10]), fabsf(s_posef[tid][11])));
     s_posef[tid][12] = fminf(fmaf(4.0e-5f, tmax, 1.0e-4f), 8.0f);
     s_vote[tid] = 0;
   }
@@ -1499,6 +1523,7 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   const int qt_group = getenv("SGTD_COLLECT_GROUP") ? std::max(1, atoi(getenv("SGTD_COLLECT_GROUP"))) : std::max(nq, 1);
   size_t o_qtk = o; o += al((size_t)qt_group * qt_ts * 8);
   size_t o_jc = o; o += al(64);
+  size_t o_pose = o; o += al((size_t)std::max(nq * k, 1) * kMaxHyp * 12 * sizeof(double));
   size_t o_jcub = o; o += al(cubj);
   SGTD_CUDA(h, h->scratch.reserve(o, st, false));
   unsigned char *S = h->scratch.p;
@@ -1660,7 +1685,9 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   if (total > 0) {
     VerifyParams W{};
     W.cands = r->cands.p; W.k = k; W.qv = qb->vert.p; W.q_off = qb->d_off.p; W.dbv = h->vert.p;
-    W.m_q = r->m_q.p; W.m_g = r->m_g.p; W.inl = r->inl.p;
+    W.m_q = r->m_q.p; W.m_g = r->m_g.p; W.inl = r->inl.p; W.pose = (double *)(S + o_pose);
+    k_hypotheses<<<(unsigned)(((size_t)nslot * kMaxHyp + 127) / 128), 128, 0, st>>>(W, (int)nslot);
+    SGTD_LAUNCHED(h);
     k_verify<<<(unsigned)nslot, kVerifyThreads, 0, st>>>(W);
     SGTD_LAUNCHED(h);
     SGTD_CUDA(h, cudaGetLastError());
