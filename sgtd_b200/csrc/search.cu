@@ -1646,11 +1646,11 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   SGTD_CUDA(h, r->m_cell.reserve(tm, st, false)); SGTD_CUDA(h, r->inl.reserve(tm, st, false));
   r->m_q.n = r->m_g.n = r->m_cell.n = r->inl.n = (size_t)total;
   if (total > 0) {
-    // The inverted form pays a fixed ~4 ms per 1,024 queries to build the per-query tables (DRAM-bound
-    // random inserts) and then ~half the per-candidate cost; with the database split over >= 4 shards a
-    // rank owns too few candidates per query to amortise it (measured: 8 shards 5.1 ms vs 2.3 ms).
+    // The inverted form pays a fixed ~1.6 ms per 1,024 queries to build the per-query tables and then
+    // ~1/4 of the per-candidate cost of k_collect; with the database split over 8 shards a rank owns too
+    // few candidates per query to amortise the fixed part, so it is used up to 4 shards.
     const char *cmode = getenv("SGTD_COLLECT_MODE");
-    const bool inverted = cmode ? strcmp(cmode, "desc") != 0 : h->nranks <= 2;
+    const bool inverted = cmode ? strcmp(cmode, "desc") != 0 : h->nranks <= 4;
     if (inverted) {
       // per-query probe multimap, then one lookup per keyframe entry + shared-memory sort
       CollectInvParams I{};

@@ -117,14 +117,15 @@ def test_search_parity(world, built):
 
 def test_vote_formulations_agree(world, built, monkeypatch):
     """The bucket-major join (default), the per-probe streaming kernel (SGTD_VOTE_MODE=stream) and
-    the join with several query groups give identical votes, counters and candidates."""
+    the join with several query groups give identical votes, counters and candidates; the inverted
+    match collection (default) and the per-descriptor one (SGTD_COLLECT_MODE=desc) identical lists."""
     mgr, o, *_ = built
     qx, ql, qo = world["queries"]
     qb = mgr.build(capi.make_nodes(qx, ql), qo)
     F = o.current_frame_id
     ref = None
-    for env in ({}, {"SGTD_VOTE_MODE": "stream"}, {"SGTD_JOIN_GROUPS": "3"}):
-        for k in ("SGTD_VOTE_MODE", "SGTD_JOIN_GROUPS"):
+    for env in ({}, {"SGTD_VOTE_MODE": "stream"}, {"SGTD_JOIN_GROUPS": "3"}, {"SGTD_COLLECT_MODE": "desc"}):
+        for k in ("SGTD_VOTE_MODE", "SGTD_JOIN_GROUPS", "SGTD_COLLECT_MODE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -132,12 +133,17 @@ def test_vote_formulations_agree(world, built, monkeypatch):
         loops, cands = res.download()
         stats, _ = res.stats()
         votes = np.stack([res.votes(q, F) for q in range(qo.shape[0] - 1)])
-        cur = (votes.tobytes(), loops.tobytes(), cands.tobytes(), stats)
+        lists = []
+        for q in range(qo.shape[0] - 1):
+            for c in range(int(loops["ncand"][q])):
+                lists.extend(a.tobytes() for a in res.matches(q, c, int(cands["nmatch"][q, c])))
+                lists.append(res.inliers(q, c, int(cands["ninlier"][q, c])).tobytes())
+        cur = (votes.tobytes(), loops.tobytes(), cands.tobytes(), stats, b"".join(lists))
         if ref is None:
             ref = cur
         else:
             assert cur[0] == ref[0] and cur[1] == ref[1] and cur[3] == ref[3]
-            assert cur[2] == ref[2]
+            assert cur[2] == ref[2] and cur[4] == ref[4]
 
 
 @pytest.mark.parametrize("over", [
