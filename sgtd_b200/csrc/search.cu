@@ -215,7 +215,7 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 //                  kVoteUnroll x 32 per trip) and tested against all probes of the run
 //                  (their side lengths / thresholds / vote rows sit in shared memory).
 // Same pair tests, same votes; HBM traffic drops by the run length.
-constexpr int kJoinSeg = 16;
+constexpr int kJoinSeg = 32;
 
 struct EmitParams2 {
   const DescRec *q; const QAux *aux; int64_t nd;
