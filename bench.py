@@ -118,15 +118,15 @@ def measured_peak():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the vote kernel from the ncu --set full
 # capture of THIS workload (profiles/r01c_ncu_summary.md); None for any other workload / sharding.
-NCU_TRAFFIC = {("k_vote_join", 100000, 1024, 1): 38.625491e9 + 4.987085e9,
+NCU_TRAFFIC = {("k_vote_join", 100000, 1024, 1): 38.498398e9 + 5.075352e9,
                ("k_vote", 100000, 1024, 1): 355.053564e9 + 20.017364e9}
 ROOFLINE_NOTE = ("achieved = SURVEY 8d per-probe byte model (32Q+16P+28E+12M, counters from the kernel) / CUDA-event "
                  "time of the vote kernel. k_vote_join streams each bucket once per run of sorted probes instead of "
                  "once per probe and reads a 16-byte packed float entry (exact FP64 only inside a proven band), so its "
-                 "real DRAM traffic (`traffic`, ncu) is ~9x below the model and `frac` exceeds 1; "
-                 "`traffic_frac_of_peak` is the HBM utilisation of the bytes actually moved -- the kernel is now "
-                 "instruction-issue bound (81 % issue-active, profiles/r01c_ncu_summary.md). "
-                 "SGTD_VOTE_MODE=stream selects the per-probe kernel the model describes (0.95 of peak, 4.5x slower).")
+                 "real DRAM traffic (`traffic`, ncu, profiles/r01f_ncu_summary.md) is ~9x below the model and `frac` "
+                 "exceeds 1; `traffic_frac_of_peak` is the HBM utilisation of the bytes actually moved (~0.7, with "
+                 "67 % issue-active: 4.8e9 vote increments per step leave as sector-coalesced REDs). "
+                 "SGTD_VOTE_MODE=stream selects the per-probe kernel the model describes (0.95 of peak, ~6x slower).")
 
 
 def result_crc(loops, cands):
