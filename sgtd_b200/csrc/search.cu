@@ -1,12 +1,15 @@
 // search.cu -- stages 3b + 4: query voting, top-k, match lists, verification.
 //
 // Replaces STDescManager::SearchLoop (R/src/STDesc.cpp:84-147):
-//   k_vote      candidate_selector's probe loop + vote array  (:351-420)
-//   k_topk      the candidate_num x argmax ranking            (:423-433)
-//   k_merge     (multi-shard) deterministic merge of per-shard top-k lists
-//   k_collect   match_triangle_list of each selected keyframe (:437-447)
-//   k_verify    candidate_verify + triangle_solver            (:462-571)
-//   k_best      best-candidate selection / icp_threshold      (:103-146)
+//   k_qaux, k_probe_emit, k_vote_join (k_vote)
+//                 candidate_selector's probe loop + vote array      (:351-420)
+//   k_topk        the candidate_num x argmax ranking                (:423-433)
+//   k_merge       (multi-shard) deterministic merge of per-shard top-k lists
+//   k_query_index, k_collect_inv (k_collect)
+//                 match_triangle_list of each selected keyframe     (:437-447)
+//   k_hypotheses  triangle_solver of every sampled match pair       (:549-571)
+//   k_verify      candidate_verify: votes, best hypothesis, inliers (:462-547)
+//   k_best        best-candidate selection / icp_threshold          (:103-146)
 //
 // All FP64 comparisons are the reference's, reformulated without changing any
 // outcome: "sqrt(x) < t" is evaluated as "x < sq_threshold(t)".
@@ -1157,13 +1160,13 @@ __device__ __forceinline__ void load_pair(const VerifyParams &P, int64_t q0, int
   b[0] = y.a.x; b[1] = y.a.y; b[2] = y.a.z; b[3] = y.b.x; b[4] = y.b.y; b[5] = y.b.z; b[6] = y.c.x; b[7] = y.c.y; b[8] = y.c.z;
 }
 
-// One CTA (4 warps) per candidate.  Threads 0..H-1 first solve the 3-point Kabsch of pair
-// h*skip (H <= 49 hypotheses) and park (R,t) in shared memory.  Then the roles are transposed:
+// k_hypotheses solves the 3-point Kabsch of pair h*skip for every hypothesis (H <= 49 per
+// candidate); k_verify then runs one CTA (4 warps) per candidate with the roles transposed:
 // a thread owns a couple of match pairs (registers, fetched once from HBM/L2) and walks the
 // hypotheses with broadcast shared-memory reads -- every lane is busy whatever H is, and
-// there is no barrier inside the scoring loop.  Votes are warp-ballot counts; the per-pair
-// outcome bits of all hypotheses are kept (64-bit mask per pair, shared memory) so that the
-// inlier list of the winning hypothesis needs no second evaluation.
+// there is no barrier inside the scoring loop.  The warp ballots of every (hypothesis, warp
+// tile) are kept in shared memory: votes are their population counts and the inlier list of
+// the winning hypothesis is read back from them, so nothing is evaluated twice.
 //
 // Hypothesis votes use an FP32 pre-filter: the residual of each vertex is first formed
 // in float (FMA).  With |coordinate|, |t| <= X the float residual components are off by
@@ -1171,16 +1174,6 @@ __device__ __forceinline__ void load_pair(const VerifyParams &P, int64_t q0, int
 // boundary; outside the band 9 +- margin(X) the float decision equals the reference's
 // FP64 decision, inside it the vertex is re-evaluated exactly in FP64.  Outcomes are
 // therefore identical to pair_inlier() for every pair (checked bit-for-bit by the tests).
-struct __align__(16) PairTile {  // 20 floats: A,B,C of the query, A',B',C' of the keyframe, max |coord|, pad
-  float4 v[5];
-};
-__device__ __forceinline__ float resid2_f32(const float *Rf, const float *tf, float px, float py, float pz, float bx,
-                                            float by, float bz) {
-  const float rx = fmaf(Rf[0], px, fmaf(Rf[1], py, fmaf(Rf[2], pz, tf[0]))) - bx;
-  const float ry = fmaf(Rf[3], px, fmaf(Rf[4], py, fmaf(Rf[5], pz, tf[1]))) - by;
-  const float rz = fmaf(Rf[6], px, fmaf(Rf[7], py, fmaf(Rf[8], pz, tf[2]))) - bz;
-  return fmaf(rx, rx, fmaf(ry, ry, rz * rz));
-}
 __device__ __forceinline__ bool vertex_inlier_fast(const float *Rf, const float *tf, const double *R, const double *t,
                                                    float px, float py, float pz, float bx, float by, float bz,
                                                    float margin) {
@@ -1197,7 +1190,7 @@ __device__ __forceinline__ bool vertex_inlier_fast(const float *Rf, const float 
   return sqn3(dx, dy, dz) < 9.0;
 }
 
-// |R p + t - b|^2 of two pairs at once; each half is an IEEE fmaf chain, so the values equal resid2_f32()'s
+// |R p + t - b|^2 of two pairs at once; each half is an IEEE fmaf chain, the same one vertex_inlier_fast() forms
 __device__ __forceinline__ f32x2 resid2_x2(const f32x2 *R2, const f32x2 *t2, f32x2 px, f32x2 py, f32x2 pz, f32x2 bx,
                                            f32x2 by, f32x2 bz) {
   const f32x2 rx = sub2(fma2(R2[0], px, fma2(R2[1], py, fma2(R2[2], pz, t2[0]))), bx);
