@@ -228,39 +228,65 @@ struct EmitParams2 {
   uint32_t group_shift, group_div;  // sort key = (query / group_div) << group_shift | slot
 };
 
+// A warp takes kEmitBatch consecutive descriptors per trip (lane = probe ordinal): the first table reads
+// of all of them are in flight together, and the output cursor -- one address for the whole grid -- is
+// advanced once per trip instead of once per descriptor.
+constexpr int kEmitBatch = 4;
 __global__ void __launch_bounds__(kVoteThreads) k_probe_emit(EmitParams2 P) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * kVoteThreads + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * kVoteThreads) >> 5;
   unsigned long long cP = 0, cPf = 0, cE = 0, cQ = 0;
-  for (int64_t d = warp; d < P.nd; d += nwarps) {
-    const DescRec r = P.q[d];
-    const QAux a = P.aux[d];
-    const bool pass = (a.mask >> lane) & 1u;
-    uint32_t slot = 0, cnt = 0;
-    if (pass) {
-      const uint64_t key = probe_cell_key(r, lane);
-      uint64_t pos = mix64(key) & P.mask;
-      while (true) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.table[pos]));
-        const uint64_t k = ((uint64_t)raw.y << 32) | raw.x;
-        if (k == key) { slot = (uint32_t)pos; cnt = raw.w; break; }
-        if (k == SGTD_EMPTY_KEY) break;
-        pos = (pos + 1) & P.mask;
-      }
-    }
-    const unsigned m_pass = __ballot_sync(0xffffffffu, pass);
-    const unsigned m_found = __ballot_sync(0xffffffffu, cnt > 0);
-    uint32_t esum = cnt;
+  for (int64_t d0 = warp * kEmitBatch; d0 < P.nd; d0 += nwarps * kEmitBatch) {
+    uint64_t key[kEmitBatch], pos[kEmitBatch];
+    uint4 raw[kEmitBatch];
+    uint32_t grp[kEmitBatch];
+    bool pass[kEmitBatch];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
-    cQ += 1; cP += __popc(m_pass); cPf += __popc(m_found); cE += esum;
+    for (int j = 0; j < kEmitBatch; ++j) {
+      const int64_t d = min(d0 + j, P.nd - 1);
+      const DescRec r = P.q[d];
+      const QAux a = P.aux[d];
+      pass[j] = (d0 + j < P.nd) && ((a.mask >> lane) & 1u);
+      grp[j] = (a.qi / P.group_div) << P.group_shift;
+      key[j] = probe_cell_key(r, lane);
+      pos[j] = mix64(key[j]) & P.mask;
+      raw[j] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+      if (pass[j]) raw[j] = __ldg(reinterpret_cast<const uint4 *>(&P.table[pos[j]]));
+    }
+    uint32_t slot[kEmitBatch], cnt[kEmitBatch];
+    unsigned m_found[kEmitBatch];
+    uint32_t total = 0;
+#pragma unroll
+    for (int j = 0; j < kEmitBatch; ++j) {
+      slot[j] = 0; cnt[j] = 0;
+      if (pass[j]) {
+        while (true) {
+          const uint64_t k = ((uint64_t)raw[j].y << 32) | raw[j].x;
+          if (k == key[j]) { slot[j] = (uint32_t)pos[j]; cnt[j] = raw[j].w; break; }
+          if (k == SGTD_EMPTY_KEY) break;
+          pos[j] = (pos[j] + 1) & P.mask;
+          raw[j] = __ldg(reinterpret_cast<const uint4 *>(&P.table[pos[j]]));
+        }
+      }
+      const unsigned m_pass = __ballot_sync(0xffffffffu, pass[j]);
+      m_found[j] = __ballot_sync(0xffffffffu, cnt[j] > 0);
+      uint32_t esum = cnt[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+      cQ += (d0 + j < P.nd); cP += __popc(m_pass); cPf += __popc(m_found[j]); cE += esum;
+      total += __popc(m_found[j]);
+    }
     unsigned long long base = 0;
-    if (lane == 0 && m_found) base = atomicAdd(P.cursor, (unsigned long long)__popc(m_found));
+    if (lane == 0 && total) base = atomicAdd(P.cursor, (unsigned long long)total);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (cnt > 0) {
-      const unsigned long long o = base + __popc(m_found & ((1u << lane) - 1u));
-      P.pkey[o] = slot | ((a.qi / P.group_div) << P.group_shift); P.pval[o] = (uint32_t)d;
+#pragma unroll
+    for (int j = 0; j < kEmitBatch; ++j) {
+      if (cnt[j] > 0) {
+        const unsigned long long o = base + __popc(m_found[j] & ((1u << lane) - 1u));
+        P.pkey[o] = slot[j] | grp[j]; P.pval[o] = (uint32_t)(d0 + j);
+      }
+      base += __popc(m_found[j]);
     }
   }
   if (lane == 0) {
