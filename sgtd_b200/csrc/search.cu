@@ -478,15 +478,21 @@ __global__ void __launch_bounds__(kTopkThreads) k_topk(const uint32_t *votes, in
   __shared__ unsigned long long s_list[kMaxCand];
   __shared__ uint32_t s_scan[kTopkThreads];
   __shared__ uint32_t s_tmp[kTopkThreads / 32];
-  __shared__ uint32_t s_prefix, s_mask, s_need, s_nlist;
+  __shared__ uint32_t s_prefix, s_mask, s_need, s_nlist, s_vmax;
   const int tid = threadIdx.x;
   const int q = blockIdx.x;
   const uint32_t *row = votes + (size_t)q * (size_t)F;
   // pass A: how many keyframes have >= 5 votes
-  uint32_t n5 = 0;
+  uint32_t n5 = 0, vmax = 0;
   unsigned long long msum = 0;
-  for (int64_t f = tid; f < F; f += kTopkThreads) { const uint32_t v = row[f]; n5 += v >= 5u; msum += v; }
+  for (int64_t f = tid; f < F; f += kTopkThreads) { const uint32_t v = row[f]; n5 += v >= 5u; msum += v; vmax = max(vmax, v); }
+  if (tid == 0) s_vmax = 0;
   n5 = block_sum<uint32_t>(n5, s_tmp);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if ((tid & 31) == 0) atomicMax(&s_vmax, vmax);
+  __syncthreads();
+  vmax = s_vmax;  // largest vote of the row
   if (m_counter) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
@@ -499,10 +505,17 @@ __global__ void __launch_bounds__(kTopkThreads) k_topk(const uint32_t *votes, in
     const int shifts[3] = {22, 11, 0};
     const int widths[3] = {10, 11, 11};
     for (int p = 0; p < 3; ++p) {
+      const uint32_t dmask = (1u << widths[p]) - 1u;
+      if ((vmax >> shifts[p]) == 0) {
+        // this digit is 0 in every vote of the row (typical rows peak at a few thousand votes): nothing to
+        // select, and a histogram would only have every thread hit the same counter
+        __syncthreads();
+        if (tid == 0) s_mask |= dmask << shifts[p];
+        continue;
+      }
       for (int i = tid; i < 2048; i += kTopkThreads) s_hist[i] = 0;
       __syncthreads();
       const uint32_t prefix = s_prefix, mask = s_mask;
-      const uint32_t dmask = (1u << widths[p]) - 1u;
       for (int64_t f = tid; f < F; f += kTopkThreads) {
         const uint32_t v = row[f];
         if ((v & mask) == prefix) atomicAdd(&s_hist[(v >> shifts[p]) & dmask], 1u);
