@@ -277,6 +277,23 @@ int sgtd_graph_read_json(const char *path, sgtd_node *nodes, int32_t cap,
 int sgtd_scan_read_kitti(const char *bin_path, const char *label_path,
                          float *points, uint32_t *labels, int64_t cap, int64_t *n);
 
+/* ---- evaluation helpers of the node's main loop (host only) ------------------------ */
+/* compute_adj_rpe (R/include/utility.hpp:110-123): delta = est^-1 * gt for two row-major
+ * 3x4 poses [R|t]; *t_err = ||delta.t||, *r_err_deg = |acos(clamp((trace(delta.R)-1)/2,
+ * -1, 1))| in degrees.  Evaluated in double (the reference forms delta in float).
+ * SGTD_E_INVALID if est's 3x3 block is singular. */
+int sgtd_pose_error(const double *gt12, const double *est12, double *t_err,
+                    double *r_err_deg);
+/* The success test of the main loop (R/src/semantic_graph_localization.cpp:724-750):
+ * estimated pose = map_pose12 (pose of the matched keyframe) * [R9|t3] (the loop
+ * transform: sgtd_candidate R, t) * extr12 (sensor extrinsic, NULL = identity), compared
+ * with gt12 by sgtd_pose_error; *success = t_err < t_max && r_err_deg < r_max_deg
+ * (reference: 5 m, 10 deg).  est12 (optional) receives the estimated pose. */
+int sgtd_localization_check(const double *map_pose12, const double *R9, const double *t3,
+                            const double *extr12, const double *gt12, double t_max,
+                            double r_max_deg, double *est12, double *t_err,
+                            double *r_err_deg, int32_t *success);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,8 @@ SYMBOLS = {
     "sgtd_graph_write_json": (C.c_int, [C.c_char_p, _VP, _I32, _VP]),
     "sgtd_graph_read_json": (C.c_int, [C.c_char_p, _VP, _I32, _VP, _VP, _VP]),
     "sgtd_scan_read_kitti": (C.c_int, [C.c_char_p, C.c_char_p, _VP, _VP, _I64, _VP]),
+    "sgtd_pose_error": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "sgtd_localization_check": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP]),
 }
 
 _lib = None
@@ -413,6 +415,34 @@ def scan_read_kitti(bin_path, label_path):
     if rc:
         raise SgtdError(rc, f"cannot read {label_path}")
     return pts, lab
+
+
+def pose_error(gt12, est12):
+    """compute_adj_rpe (R/include/utility.hpp:110-123) for two row-major 3x4 poses -> (t_err, r_err_deg)."""
+    gt = np.ascontiguousarray(gt12, np.float64).reshape(12)
+    est = np.ascontiguousarray(est12, np.float64).reshape(12)
+    te, re = C.c_double(0), C.c_double(0)
+    rc = lib().sgtd_pose_error(_p(gt), _p(est), C.byref(te), C.byref(re))
+    if rc:
+        raise SgtdError(rc, "sgtd_pose_error")
+    return te.value, re.value
+
+
+def localization_check(map_pose12, R9, t3, gt12, extr12=None, t_max=5.0, r_max_deg=10.0):
+    """The main loop's success test (R/src/semantic_graph_localization.cpp:724-750)
+    -> (success, t_err, r_err_deg, est12)."""
+    mp = np.ascontiguousarray(map_pose12, np.float64).reshape(12)
+    R = np.ascontiguousarray(R9, np.float64).reshape(9)
+    t = np.ascontiguousarray(t3, np.float64).reshape(3)
+    gt = np.ascontiguousarray(gt12, np.float64).reshape(12)
+    ex = None if extr12 is None else np.ascontiguousarray(extr12, np.float64).reshape(12)
+    est = np.zeros(12, np.float64)
+    te, re, ok = C.c_double(0), C.c_double(0), C.c_int32(0)
+    rc = lib().sgtd_localization_check(_p(mp), _p(R), _p(t), None if ex is None else _p(ex), _p(gt), t_max, r_max_deg,
+                                       _p(est), C.byref(te), C.byref(re), C.byref(ok))
+    if rc:
+        raise SgtdError(rc, "sgtd_localization_check")
+    return bool(ok.value), te.value, re.value, est
 
 
 def nccl_unique_id():

@@ -9,6 +9,7 @@
 // float -> JSON double -> float round-trips exactly (the reference relies on the same).
 // Plain C++ (no device code); lives in the library so a C++ host needs nothing else.
 #include <cerrno>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -170,6 +171,67 @@ int sgtd_scan_read_kitti(const char *bin_path, const char *label_path, float *po
   else if ((int64_t)fread(labels, 4, (size_t)nl, fl) != nl) rc = SGTD_E_IO;
   fclose(fl);
   return rc;
+}
+
+// ---- evaluation helpers (host only) ----------------------------------------------------------
+namespace {
+// c = a * b for row-major 3x4 rigid/affine transforms with an implied last row (0, 0, 0, 1)
+void mul34(const double *a, const double *b, double *c) {
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 4; ++j) {
+      double v = (j == 3) ? a[i * 4 + 3] : 0.0;
+      for (int k = 0; k < 3; ++k) v += a[i * 4 + k] * b[k * 4 + j];
+      c[i * 4 + j] = v;
+    }
+  }
+}
+// inverse of a row-major 3x4 transform (general 3x3 block, not assumed orthonormal); false if singular
+bool inv34(const double *a, double *o) {
+  const double m00 = a[0], m01 = a[1], m02 = a[2], m10 = a[4], m11 = a[5], m12 = a[6], m20 = a[8], m21 = a[9], m22 = a[10];
+  const double c00 = m11 * m22 - m12 * m21, c01 = m12 * m20 - m10 * m22, c02 = m10 * m21 - m11 * m20;
+  const double det = m00 * c00 + m01 * c01 + m02 * c02;
+  if (det == 0.0 || det != det) return false;
+  const double id = 1.0 / det;
+  double r[9];
+  r[0] = c00 * id; r[1] = (m02 * m21 - m01 * m22) * id; r[2] = (m01 * m12 - m02 * m11) * id;
+  r[3] = c01 * id; r[4] = (m00 * m22 - m02 * m20) * id; r[5] = (m02 * m10 - m00 * m12) * id;
+  r[6] = c02 * id; r[7] = (m01 * m20 - m00 * m21) * id; r[8] = (m00 * m11 - m01 * m10) * id;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) o[i * 4 + j] = r[i * 3 + j];
+    o[i * 4 + 3] = -(r[i * 3] * a[3] + r[i * 3 + 1] * a[7] + r[i * 3 + 2] * a[11]);
+  }
+  return true;
+}
+}  // namespace
+
+int sgtd_pose_error(const double *gt12, const double *est12, double *t_err, double *r_err_deg) {
+  if (!gt12 || !est12 || !t_err || !r_err_deg) return SGTD_E_INVALID;
+  double inv[12], d[12];
+  if (!inv34(est12, inv)) return SGTD_E_INVALID;
+  mul34(inv, gt12, d);  // delta_T = lo.inverse() * gt (utility.hpp:114)
+  *t_err = sqrt(d[3] * d[3] + d[7] * d[7] + d[11] * d[11]);
+  const double c = fmin(fmax((d[0] + d[5] + d[10] - 1.0) / 2.0, -1.0), 1.0);
+  *r_err_deg = fabs(acos(c)) / M_PI * 180.0;
+  return SGTD_OK;
+}
+
+int sgtd_localization_check(const double *map_pose12, const double *R9, const double *t3, const double *extr12,
+                            const double *gt12, double t_max, double r_max_deg, double *est12, double *t_err,
+                            double *r_err_deg, int32_t *success) {
+  if (!map_pose12 || !R9 || !t3 || !gt12 || !t_err || !r_err_deg || !success) return SGTD_E_INVALID;
+  double loop[12], a[12], est[12];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) loop[i * 4 + j] = R9[i * 3 + j];
+    loop[i * 4 + 3] = t3[i];
+  }
+  mul34(map_pose12, loop, a);  // transform_j1 * new_trans (semantic_graph_localization.cpp:742)
+  if (extr12) mul34(a, extr12, est);
+  else memcpy(est, a, sizeof(est));
+  if (est12) memcpy(est12, est, sizeof(est));
+  const int rc = sgtd_pose_error(gt12, est, t_err, r_err_deg);
+  if (rc != SGTD_OK) return rc;
+  *success = (*t_err < t_max && *r_err_deg < r_max_deg) ? 1 : 0;  // :745
+  return SGTD_OK;
 }
 
 }  // extern "C"

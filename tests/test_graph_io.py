@@ -58,3 +58,55 @@ def test_kitti_scan_files(tmp_path):
     lab[:-1].tofile(l)
     with pytest.raises(capi.SgtdError):
         capi.scan_read_kitti(b, l)              # assert(points.cols()==labels.size())
+
+
+def _T(pose12):
+    return np.vstack([np.asarray(pose12, np.float64).reshape(3, 4), [0, 0, 0, 1]])
+
+
+def _rand_pose(rng):
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return np.column_stack([q, rng.normal(0, 50, 3)]).reshape(12)
+
+
+def test_pose_error_matches_compute_adj_rpe():
+    """sgtd_pose_error against the formula of compute_adj_rpe (R/include/utility.hpp:110-123)."""
+    rng = np.random.default_rng(8)
+    for _ in range(50):
+        gt, est = _rand_pose(rng), _rand_pose(rng)
+        d = np.linalg.inv(_T(est)) @ _T(gt)
+        t_ref = np.linalg.norm(d[:3, 3])
+        r_ref = abs(np.degrees(np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1))))
+        t, r = capi.pose_error(gt, est)
+        assert abs(t - t_ref) < 1e-9 and abs(r - r_ref) < 1e-6
+    t, r = capi.pose_error(gt, gt)
+    assert t < 1e-9 and r < 1e-5
+    with pytest.raises(capi.SgtdError):
+        capi.pose_error(gt, np.zeros(12))      # singular estimate
+
+
+def test_localization_check_is_the_main_loops_success_test():
+    """T_est = T_map[match] * [R|t]_loop * extrinsic; success iff T < 5 m and R < 10 deg
+    (R/src/semantic_graph_localization.cpp:724-750)."""
+    rng = np.random.default_rng(9)
+    n_ok = 0
+    for i in range(40):
+        mp, gt, ex = _rand_pose(rng), _rand_pose(rng), _rand_pose(rng)
+        # a loop transform that reproduces gt up to a perturbation of growing size
+        want = np.linalg.inv(_T(mp)) @ _T(gt) @ np.linalg.inv(_T(ex))
+        ang = np.radians(0.5 * i)
+        c, s_ = np.cos(ang), np.sin(ang)
+        pert = np.array([[c, -s_, 0, 0.2 * i], [s_, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+        loop = want @ pert
+        ok, t, r, est = capi.localization_check(mp, loop[:3, :3], loop[:3, 3], gt, extr12=ex)
+        T_est = _T(mp) @ loop @ _T(ex)
+        assert np.allclose(_T(est), T_est, atol=1e-9)
+        t_ref, r_ref = capi.pose_error(gt, T_est[:3].reshape(12))
+        assert abs(t - t_ref) < 1e-9 and abs(r - r_ref) < 1e-9
+        assert ok == (t < 5.0 and r < 10.0)
+        n_ok += ok
+    assert 0 < n_ok < 40                        # both outcomes were exercised
+    ok, t, r, _ = capi.localization_check(mp, np.eye(3), np.zeros(3), mp)   # no extrinsic, exact pose
+    assert ok and t < 1e-9 and r < 1e-5
