@@ -1,8 +1,11 @@
 /*
  * dcvc_oracle.cpp -- CPU oracle for stage 1 (semantic instance extraction).
  *
- * TEST INFRASTRUCTURE ONLY (see sgtd_oracle.h).  PARITY UNPINNED: no reference
- * tests / golden vectors exist for this path; this is a literal, per-point
+ * TEST INFRASTRUCTURE ONLY (see sgtd_oracle.h).  The clusterManager part is pinned
+ * against the reference's own cluster_manager.hpp compiled into oracle/_ref
+ * (tests/test_reference_build.py: label_info of every point and the clusters_ order);
+ * gen_labels / gen_graphs are anchored on source lines only (get_json.cpp pulls in the
+ * whole node: Python.h, ikd-Tree, fast_gicp, matplotlib).  Literal, per-point
  * restatement of
  *   gen_labels            R/src/get_json.cpp:41-229
  *   gen_graphs            R/src/get_json.cpp:231-343   (node part, :249-299)
@@ -52,7 +55,7 @@ struct ClusterManager {
     polarCor.assign(totalSize, {0.0, 0.0, 0.0});
     for (size_t i = 0; i < totalSize; ++i) {
       double cx = selected_points_[i][0], cy = selected_points_[i][1], cz = selected_points_[i][2];
-      double r = std::sqrt((cx * cx + cy * cy) + cz * cz); /* Eigen norm() */
+      double r = std::sqrt(cx * cx + (cy * cy + cz * cz)); /* Eigen norm(): e0 + (e1 + e2), see sgtd_oracle.cpp norm3 */
       double pitch = std::asin(cz / r) * 180.0 / M_PI;
       double az = azimuthCal(cx, cy);
       if (r >= 120.0 || r <= 0.5) continue;

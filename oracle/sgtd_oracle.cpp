@@ -59,8 +59,10 @@ inline int cbe(int a, int b, int c) {
 }
 
 inline double norm3(double x, double y, double z) {
-  /* Eigen Vector3d::norm(): sqrt((x*x + y*y) + z*z) */
-  return std::sqrt((x * x + y * y) + z * z);
+  /* Eigen Vector3d::norm() = sqrt(cwiseAbs2().sum()); a fixed-size reduction of three terms is
+   * unrolled as e0 + (e1 + e2) (Eigen 3.3 Redux.h, redux_novec_unroller: halves of len/2 and
+   * len - len/2) -- the order oracle/shim/Eigen/Core gives the reference build in oracle/_ref. */
+  return std::sqrt(x * x + (y * y + z * z));
 }
 
 } // namespace
@@ -200,12 +202,13 @@ void jacobi_svd3(const double A[9], double U[9], double sv[3], double V[9]) {
   }
 }
 
-/* C = A * B^T, coefficient-wise ((a0*b0 + a1*b1) + a2*b2). */
+/* C = A * B^T: Eigen's coefficient-based small product, each coefficient the reduction
+ * a0*b0 + (a1*b1 + a2*b2) (same unrolled tree as norm3). */
 inline void mul_abt(const double A[9], const double B[9], double C[9]) {
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j)
-      C[i * 3 + j] = (A[i * 3 + 0] * B[j * 3 + 0] + A[i * 3 + 1] * B[j * 3 + 1]) +
-                     A[i * 3 + 2] * B[j * 3 + 2];
+      C[i * 3 + j] = A[i * 3 + 0] * B[j * 3 + 0] +
+                     (A[i * 3 + 1] * B[j * 3 + 1] + A[i * 3 + 2] * B[j * 3 + 2]);
 }
 inline double det3(const double m[9]) {
   return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
@@ -213,7 +216,7 @@ inline double det3(const double m[9]) {
 }
 inline void matvec(const double R[9], const double v[3], double o[3]) {
   for (int i = 0; i < 3; ++i)
-    o[i] = (R[i * 3 + 0] * v[0] + R[i * 3 + 1] * v[1]) + R[i * 3 + 2] * v[2];
+    o[i] = R[i * 3 + 0] * v[0] + (R[i * 3 + 1] * v[1] + R[i * 3 + 2] * v[2]);
 }
 
 /* triangle_solver, R/src/STDesc.cpp:549-571 */

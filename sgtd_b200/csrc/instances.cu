@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kS1Threads) k_dcvc_prepare(S1Buffers B, double
   for (int r = tid; r < t.npts; r += kS1Threads) {
     const float4 p = B.pts[t.pt0 + B.cls_idx[t.idx_off + r]];
     const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
-    const double rng = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+    const double rng = sqrt(__dadd_rn(__dmul_rn(x, x), __dadd_rn(__dmul_rn(y, y), __dmul_rn(z, z))));  // Eigen norm(): e0 + (e1 + e2)
     const double pitch = __dmul_rn(asin(z / rng), 180.0) / kPi;
     const double ang = atan2(y, x);
     const double az = ang > 0.0 ? __dmul_rn(ang, 180.0) / kPi : __dmul_rn(__dadd_rn(ang, __dmul_rn(2.0, kPi)), 180.0) / kPi;

@@ -43,11 +43,14 @@ struct VoteParams {
   unsigned long long *counters;  // Q,P,Pfound,E,M
 };
 
+// Eigen evaluates a fixed-size reduction of three terms as e0 + (e1 + e2) (Redux.h, redux_novec_unroller
+// splits [0,3) into [0,1) and [1,3)); Vector3d::norm(), squaredNorm() and the coefficients of the small
+// matrix products of triangle_solver / candidate_verify all go through it.
 __device__ __forceinline__ double norm3(double x, double y, double z) {
-  return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+  return __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dadd_rn(__dmul_rn(y, y), __dmul_rn(z, z))));
 }
 __device__ __forceinline__ double sqn3(double x, double y, double z) {
-  return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+  return __dadd_rn(__dmul_rn(x, x), __dadd_rn(__dmul_rn(y, y), __dmul_rn(z, z)));
 }
 
 // probe `ord` (0..26, x outermost) of a query descriptor: the STDesc_LOC it
@@ -1120,7 +1123,7 @@ __device__ void svd3(const double *A, double *U, double *V) {
 }
 
 __device__ __forceinline__ double dot3s(double a0, double b0, double a1, double b1, double a2, double b2) {
-  return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+  return __dadd_rn(__dmul_rn(a0, b0), __dadd_rn(__dmul_rn(a1, b1), __dmul_rn(a2, b2)));  // e0 + (e1 + e2), see norm3
 }
 
 // triangle_solver (STDesc.cpp:549-571).  sv/rv: 9 floats A,B,C of source / reference.

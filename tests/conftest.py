@@ -17,3 +17,15 @@ def oracle_lib():
     from oracle import orc
     orc.build()
     return orc
+
+
+@pytest.fixture(scope="session")
+def reference_lib():
+    """oracle/_ref/libsgtd_ref.so: the reference's own STDesc.cpp / cluster_manager.hpp compiled
+    against the oracle/shim stand-in headers.  Built here when /root/reference exists, otherwise the
+    prebuilt file that ships with the snapshot is used; skipped only if neither is there."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    ref.lib()
+    return ref
