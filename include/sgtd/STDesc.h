@@ -232,6 +232,7 @@ class STDescManager {
   explicit STDescManager(ConfigSetting &config_setting, int device = 0) : config_setting_(config_setting) {
     sgtd_config c = sgtd_detail::to_c(config_setting);
     if (sgtd_create(&c, device, &h_) != SGTD_OK) throw std::runtime_error(sgtd_last_error(nullptr));
+    k_ = c.candidate_num;  // the handle keeps the values it was created with; config_setting_ stays editable like the reference's
   }
   ~STDescManager() { sgtd_destroy(h_); }
   STDescManager(const STDescManager &) = delete;
@@ -247,22 +248,20 @@ class STDescManager {
       nodes[i] = sgtd_node{p.x, p.y, p.z, (std::uint32_t)p.label};
     }
     const std::int64_t off[2] = {0, (std::int64_t)nodes.size()};
-    sgtd_desc_batch *b = nullptr;
-    int rc = sgtd_build_descriptors(h_, nodes.data(), off, 1, nullptr, &b);
-    if (rc == SGTD_E_TOO_FEW_NODES) return;  // the reference reads stale kNN indices here (UB); yield no descriptors
-    check(rc);
-    std::vector<sgtd_desc> d((std::size_t)sgtd_desc_batch_size(b));
-    check(sgtd_desc_batch_download(h_, b, d.data(), nullptr));
-    sgtd_desc_batch_free(b);
+    Batch b;
+    // fewer nodes than descriptor_near_num: the reference reads stale kNN indices (UB); the library yields no descriptors
+    check(sgtd_build_descriptors(h_, nodes.data(), off, 1, nullptr, &b.p));
+    std::vector<sgtd_desc> d((std::size_t)sgtd_desc_batch_size(b.p));
+    check(sgtd_desc_batch_download(h_, b.p, d.data(), nullptr));
     stds_vec.reserve(d.size());
     for (const auto &x : d) stds_vec.push_back(sgtd_detail::to_std(x));
   }
 
   // add descriptors of one keyframe to the database
   void AddSTDescs(const std::vector<STDesc> &stds_vec) {
-    sgtd_desc_batch *b = upload(stds_vec);
-    check(sgtd_add_descriptors(h_, b));
-    sgtd_desc_batch_free(b);
+    Batch b;
+    upload(stds_vec, b);
+    check(sgtd_add_descriptors(h_, b.p));
     current_frame_id_ = sgtd_current_frame_id(h_);
   }
 
@@ -274,12 +273,13 @@ class STDescManager {
       loop_result = std::pair<int, double>(-1, 0);
       return;
     }
-    sgtd_desc_batch *b = upload(stds_vec);
-    sgtd_search_result *r = nullptr;
-    check(sgtd_search(h_, b, &r));
-    const int k = config_setting_.candidate_num_;
+    Batch b;
+    upload(stds_vec, b);
+    Result res_guard;
+    check(sgtd_search(h_, b.p, &res_guard.p));
+    sgtd_search_result *r = res_guard.p;
     sgtd_loop_result lr;
-    std::vector<sgtd_candidate> cands((std::size_t)k);
+    std::vector<sgtd_candidate> cands((std::size_t)k_);  // sized by the handle's candidate_num, not the editable field
     check(sgtd_result_download(h_, r, &lr, cands.data()));
     sgtd_timings tm;
     check(sgtd_result_stats(h_, r, nullptr, &tm));
@@ -317,21 +317,33 @@ class STDescManager {
     } else {
       loop_result = std::pair<int, double>(-1, 0);
     }
-    sgtd_result_free(r);
-    sgtd_desc_batch_free(b);
   }
 
  private:
   sgtd_handle *h_ = nullptr;
+  int k_ = 0;  // candidate_num the handle was created with
+  // device objects are released on every path, including the throwing ones
+  struct Batch {
+    sgtd_desc_batch *p = nullptr;
+    Batch() = default;
+    Batch(const Batch &) = delete;
+    Batch &operator=(const Batch &) = delete;
+    ~Batch() { if (p) sgtd_desc_batch_free(p); }
+  };
+  struct Result {
+    sgtd_search_result *p = nullptr;
+    Result() = default;
+    Result(const Result &) = delete;
+    Result &operator=(const Result &) = delete;
+    ~Result() { if (p) sgtd_result_free(p); }
+  };
   void check(int rc) {
     if (rc != SGTD_OK) throw std::runtime_error(sgtd_last_error(h_));
   }
-  sgtd_desc_batch *upload(const std::vector<STDesc> &v) {
+  void upload(const std::vector<STDesc> &v, Batch &b) {
     std::vector<sgtd_desc> d(v.size());
     for (std::size_t i = 0; i < v.size(); ++i) d[i] = sgtd_detail::from_std(v[i]);
     const std::int64_t off[2] = {0, (std::int64_t)d.size()};
-    sgtd_desc_batch *b = nullptr;
-    check(sgtd_desc_batch_upload(h_, d.data(), off, 1, &b));
-    return b;
+    check(sgtd_desc_batch_upload(h_, d.data(), off, 1, &b.p));
   }
 };

@@ -41,13 +41,14 @@
 extern "C" {
 #endif
 
-#define SGTD_ABI_VERSION 1
+#define SGTD_ABI_VERSION 2
 
 typedef enum sgtd_status {
   SGTD_OK = 0,
   SGTD_E_INVALID = 1,       /* bad argument                                   */
-  SGTD_E_TOO_FEW_NODES = 2, /* a scan has fewer nodes than descriptor_near_num
-                               (the reference reads stale indices here)       */
+  SGTD_E_TOO_FEW_NODES = 2, /* reserved (ABI 1 returned it for a scan with fewer
+                               nodes than descriptor_near_num; such a scan now
+                               yields zero descriptors and keeps its slot)    */
   SGTD_E_CAPACITY = 3,      /* a caller-provided buffer is too small          */
   SGTD_E_CUDA = 4,          /* CUDA runtime error, see sgtd_last_error        */
   SGTD_E_NCCL = 5,
@@ -166,7 +167,11 @@ int64_t sgtd_kernel_launches(const sgtd_handle *h);   /* kernels launched so far
 /* ---- stage 2: triangle descriptors --------------------------------------- */
 /* nodes of scan s are nodes[scan_offsets[s] .. scan_offsets[s+1]).  frame_ids
  * may be NULL: every descriptor then carries current_frame_id_ (what
- * BuildSingleScanSTD does).  The result stays on the device. */
+ * BuildSingleScanSTD does).  A scan with fewer nodes than descriptor_near_num
+ * (including an empty one) yields zero descriptors and keeps its slot in the
+ * batch, so keyframe ids stay aligned with the caller's scans (the reference
+ * reads stale kNN indices in that case, R/src/STDesc.cpp:186-197).  The result
+ * stays on the device. */
 int sgtd_build_descriptors(sgtd_handle *h, const sgtd_node *nodes,
                            const int64_t *scan_offsets, int32_t nscans,
                            const uint32_t *frame_ids, sgtd_desc_batch **out);
@@ -285,14 +290,26 @@ int sgtd_scan_read_kitti(const char *bin_path, const char *label_path,
 int sgtd_pose_error(const double *gt12, const double *est12, double *t_err,
                     double *r_err_deg);
 /* The success test of the main loop (R/src/semantic_graph_localization.cpp:724-750):
- * estimated pose = map_pose12 (pose of the matched keyframe) * [R9|t3] (the loop
- * transform: sgtd_candidate R, t) * extr12 (sensor extrinsic, NULL = identity), compared
- * with gt12 by sgtd_pose_error; *success = t_err < t_max && r_err_deg < r_max_deg
- * (reference: 5 m, 10 deg).  est12 (optional) receives the estimated pose. */
+ *   MAt = transform_j1 * new_trans * transformation     vs     transform_test * BASE2OUSTER
+ * estimated pose = map_pose12 (pose of the matched keyframe) * [R9|t3] (the loop transform:
+ * sgtd_candidate R, t) * refine12 (the GICP refinement `transformation`; NULL = identity, i.e.
+ * GICP disabled); ground truth = gt12 * gt_extr12 (BASE2OUSTER; NULL = identity).  The two are
+ * compared by sgtd_pose_error; *success = t_err < t_max && r_err_deg < r_max_deg (reference: 5 m,
+ * 10 deg).  est12 (optional) receives the estimated pose. */
 int sgtd_localization_check(const double *map_pose12, const double *R9, const double *t3,
-                            const double *extr12, const double *gt12, double t_max,
-                            double r_max_deg, double *est12, double *t_err,
+                            const double *refine12, const double *gt12, const double *gt_extr12,
+                            double t_max, double r_max_deg, double *est12, double *t_err,
                             double *r_err_deg, int32_t *success);
+/* recall@k bookkeeping of the main loop (R/src/semantic_graph_localization.cpp:603-646): orders the
+ * ncand candidates of one query by score (match_fitness) descending -- ties keep candidate order; the
+ * reference's std::sort leaves them unspecified -- and returns in *rank the position of the first one
+ * whose keyframe pose (map_poses12 + 12 * frame, row-major 3x4) lies within `radius` (reference: 10 m,
+ * translation part of compute_adj_rpe) of the query's ground-truth pose gt12, or -1 if none does:
+ * the bin of the reference's STD_num[] histogram.  order (optional, ncand entries) receives the
+ * sorted candidate indices. */
+int sgtd_recall_rank(const sgtd_candidate *cands, int32_t ncand, const double *map_poses12,
+                     int64_t n_map, const double *gt12, double radius, int32_t *rank,
+                     int32_t *order);
 
 #ifdef __cplusplus
 }

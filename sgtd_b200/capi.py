@@ -95,7 +95,8 @@ SYMBOLS = {
     "sgtd_graph_read_json": (C.c_int, [C.c_char_p, _VP, _I32, _VP, _VP, _VP]),
     "sgtd_scan_read_kitti": (C.c_int, [C.c_char_p, C.c_char_p, _VP, _VP, _I64, _VP]),
     "sgtd_pose_error": (C.c_int, [_VP, _VP, _VP, _VP]),
-    "sgtd_localization_check": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP]),
+    "sgtd_localization_check": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP]),
+    "sgtd_recall_rank": (C.c_int, [_VP, C.c_int32, _VP, C.c_int64, _VP, C.c_double, _VP, _VP]),
 }
 
 _lib = None
@@ -428,21 +429,38 @@ def pose_error(gt12, est12):
     return te.value, re.value
 
 
-def localization_check(map_pose12, R9, t3, gt12, extr12=None, t_max=5.0, r_max_deg=10.0):
-    """The main loop's success test (R/src/semantic_graph_localization.cpp:724-750)
+def localization_check(map_pose12, R9, t3, gt12, refine12=None, gt_extr12=None, t_max=5.0, r_max_deg=10.0):
+    """The main loop's success test (R/src/semantic_graph_localization.cpp:724-750):
+    map pose * loop transform * refinement  vs  ground truth * extrinsic
     -> (success, t_err, r_err_deg, est12)."""
     mp = np.ascontiguousarray(map_pose12, np.float64).reshape(12)
     R = np.ascontiguousarray(R9, np.float64).reshape(9)
     t = np.ascontiguousarray(t3, np.float64).reshape(3)
     gt = np.ascontiguousarray(gt12, np.float64).reshape(12)
-    ex = None if extr12 is None else np.ascontiguousarray(extr12, np.float64).reshape(12)
+    rf = None if refine12 is None else np.ascontiguousarray(refine12, np.float64).reshape(12)
+    ex = None if gt_extr12 is None else np.ascontiguousarray(gt_extr12, np.float64).reshape(12)
     est = np.zeros(12, np.float64)
     te, re, ok = C.c_double(0), C.c_double(0), C.c_int32(0)
-    rc = lib().sgtd_localization_check(_p(mp), _p(R), _p(t), None if ex is None else _p(ex), _p(gt), t_max, r_max_deg,
+    rc = lib().sgtd_localization_check(_p(mp), _p(R), _p(t), None if rf is None else _p(rf), _p(gt),
+                                       None if ex is None else _p(ex), t_max, r_max_deg,
                                        _p(est), C.byref(te), C.byref(re), C.byref(ok))
     if rc:
         raise SgtdError(rc, "sgtd_localization_check")
     return bool(ok.value), te.value, re.value, est
+
+
+def recall_rank(cands, map_poses12, gt12, radius=10.0):
+    """recall@k bookkeeping (R/src/semantic_graph_localization.cpp:603-646) for one query's candidates
+    (structured CAND_DTYPE array, valid entries only) -> (rank or -1, candidate order by fitness)."""
+    cands = np.ascontiguousarray(cands, CAND_DTYPE)
+    mp = np.ascontiguousarray(map_poses12, np.float64).reshape(-1, 12)
+    gt = np.ascontiguousarray(gt12, np.float64).reshape(12)
+    rank = C.c_int32(-1)
+    order = np.zeros(max(len(cands), 1), np.int32)
+    rc = lib().sgtd_recall_rank(_p(cands), len(cands), _p(mp), mp.shape[0], _p(gt), radius, C.byref(rank), _p(order))
+    if rc:
+        raise SgtdError(rc, "sgtd_recall_rank")
+    return rank.value, order[:len(cands)]
 
 
 def nccl_unique_id():

@@ -96,6 +96,9 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_pass1(BuildParams P) {
   for (int s = blockIdx.x; s < P.nscans; s += gridDim.x) {
     const int64_t n0 = P.node_off[s];
     const int K = (int)(P.node_off[s + 1] - n0);
+    // fewer nodes than descriptor_near_num (the reference reads stale kNN indices here): the scan keeps
+    // its slot in the batch and yields no descriptor (counts[s] stays 0)
+    if (K < P.near_num) continue;
     uint16_t *s_nn = reinterpret_cast<uint16_t *>(s_node + K);
     __syncthreads();
     for (int i = tid; i < K; i += kBuildThreads) {
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_pass2(EmitParams P) {
   for (int s = blockIdx.x; s < P.nscans; s += gridDim.x) {
     const int64_t n0 = P.node_off[s];
     const int K = (int)(P.node_off[s + 1] - n0);
-    const int T = K * P.npairs;
+    const int T = K < P.near_num ? 0 : K * P.npairs;
     const int64_t w0 = P.word_off[s];
     int64_t base = P.desc_off[s];
     const uint32_t frame = P.frame_ids[s];
@@ -275,7 +278,7 @@ int build_descriptors(sgtd_handle *h, const sgtd_node *d_nodes, const std::vecto
   std::vector<int64_t> word_off(nscans + 1, 0);
   for (int s = 0; s < nscans; ++s) {
     int64_t K = off[s + 1] - off[s];
-    if (K < near_num) SGTD_FAIL(h, SGTD_E_TOO_FEW_NODES, "scan has fewer nodes than descriptor_near_num");
+    if (K < near_num) { word_off[s + 1] = word_off[s]; continue; }  // sparse / empty scan: zero descriptors
     if (K > kMaxNodes) SGTD_FAIL(h, SGTD_E_INVALID, "scan has more than 4096 nodes");
     if (K > Kmax) Kmax = (int)K;
     word_off[s + 1] = word_off[s] + (K * npairs + 31) / 32;

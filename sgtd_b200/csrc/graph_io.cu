@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
 #include "internal.cuh"
 
 namespace {
@@ -215,22 +217,48 @@ int sgtd_pose_error(const double *gt12, const double *est12, double *t_err, doub
   return SGTD_OK;
 }
 
-int sgtd_localization_check(const double *map_pose12, const double *R9, const double *t3, const double *extr12,
-                            const double *gt12, double t_max, double r_max_deg, double *est12, double *t_err,
-                            double *r_err_deg, int32_t *success) {
+int sgtd_localization_check(const double *map_pose12, const double *R9, const double *t3, const double *refine12,
+                            const double *gt12, const double *gt_extr12, double t_max, double r_max_deg,
+                            double *est12, double *t_err, double *r_err_deg, int32_t *success) {
   if (!map_pose12 || !R9 || !t3 || !gt12 || !t_err || !r_err_deg || !success) return SGTD_E_INVALID;
-  double loop[12], a[12], est[12];
+  double loop[12], a[12], est[12], gt[12];
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j) loop[i * 4 + j] = R9[i * 3 + j];
     loop[i * 4 + 3] = t3[i];
   }
   mul34(map_pose12, loop, a);  // transform_j1 * new_trans (semantic_graph_localization.cpp:742)
-  if (extr12) mul34(a, extr12, est);
+  if (refine12) mul34(a, refine12, est);  // ... * transformation (the GICP refinement; identity when GICP is off)
   else memcpy(est, a, sizeof(est));
+  if (gt_extr12) mul34(gt12, gt_extr12, gt);  // transform_test = transform_test * BASE2OUSTER (:741)
+  else memcpy(gt, gt12, sizeof(gt));
   if (est12) memcpy(est12, est, sizeof(est));
-  const int rc = sgtd_pose_error(gt12, est, t_err, r_err_deg);
+  const int rc = sgtd_pose_error(gt, est, t_err, r_err_deg);
   if (rc != SGTD_OK) return rc;
   *success = (*t_err < t_max && *r_err_deg < r_max_deg) ? 1 : 0;  // :745
+  return SGTD_OK;
+}
+
+// recall@k bookkeeping of the main loop (semantic_graph_localization.cpp:603-646): the candidates are
+// ordered by match_fitness descending and walked until one lies within `radius` (10 m there) of the query's
+// ground-truth pose; that position is the bin of STD_num[] that gets incremented.  The reference orders
+// with std::sort (introsort, not stable), so the order among EQUAL fitness values is unspecified there;
+// here ties keep candidate order (std::stable_sort).
+int sgtd_recall_rank(const sgtd_candidate *cands, int32_t ncand, const double *map_poses12, int64_t n_map,
+                     const double *gt12, double radius, int32_t *rank, int32_t *order) {
+  if (!cands || ncand < 0 || !map_poses12 || !gt12 || !rank) return SGTD_E_INVALID;
+  std::vector<int32_t> idx((size_t)ncand);
+  for (int32_t i = 0; i < ncand; ++i) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return cands[a].score > cands[b].score; });
+  *rank = -1;
+  for (int32_t i = 0; i < ncand; ++i) {
+    if (order) order[i] = idx[i];
+    const int32_t f = cands[idx[i]].frame;
+    if (*rank >= 0 || f < 0 || f >= n_map) continue;
+    double t_e, r_e;
+    // compute_adj_rpe(transform_t1 = query ground truth, transform1 = pose of keyframe match_id) (:637)
+    if (sgtd_pose_error(gt12, map_poses12 + (size_t)f * 12, &t_e, &r_e) != SGTD_OK) continue;
+    if (t_e < radius) *rank = i;
+  }
   return SGTD_OK;
 }
 

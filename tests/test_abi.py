@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, missing
     assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
-    assert capi.lib().sgtd_abi_version() == 1
+    assert capi.lib().sgtd_abi_version() == 2
 
 
 def test_struct_layouts_match_header(tmp_path):

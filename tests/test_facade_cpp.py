@@ -13,17 +13,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBDIR = os.path.join(ROOT, "sgtd_b200", "lib")
 
 
-def _compile(tmp_path):
-    exe = str(tmp_path / "facade_node")
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "facade_node.cpp"), "-o", exe,
+def _compile(tmp_path, eigen_like=False):
+    """eigen_like: resolve <Eigen/Core>, <pcl/...>, <ros/ros.h> to the Eigen/PCL/ROS-like headers of
+    oracle/shim (the ones the reference's own sources compile against in oracle/_ref), so that the facade
+    takes its SGTD_HAVE_EIGEN / _PCL / _ROS branches and the node's Eigen expressions (block<3,3>, <<,
+    cast<float>, products) run on the facade's STDesc / LOOP_RESULT types.  Otherwise: its POD stand-ins."""
+    exe = str(tmp_path / ("facade_node_eigen" if eigen_like else "facade_node"))
+    extra = ["-I", os.path.join(ROOT, "oracle", "shim")] if eigen_like else []
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include")] + extra +
+                          [os.path.join(ROOT, "tests", "cpp", "facade_node.cpp"), "-o", exe,
                            "-L", LIBDIR, "-lsgtd_b200", f"-Wl,-rpath,{LIBDIR}"])
     return exe
 
 
-def test_facade_compiles_and_fails_loudly_without_gpu(tmp_path):
+@pytest.mark.parametrize("eigen_like", [False, True])
+def test_facade_compiles_and_fails_loudly_without_gpu(tmp_path, eigen_like):
     capi.lib()
-    exe = _compile(tmp_path)
+    exe = _compile(tmp_path, eigen_like)
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
@@ -35,8 +41,9 @@ def test_facade_compiles_and_fails_loudly_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-def test_facade_reproduces_oracle(tmp_path, oracle_lib):
-    exe = _compile(tmp_path)
+@pytest.mark.parametrize("eigen_like", [False, True])
+def test_facade_reproduces_oracle(tmp_path, oracle_lib, eigen_like):
+    exe = _compile(tmp_path, eigen_like)
     cfg = synth.make_config(0, 40, 2)
     xyz, lab, off = cfg["db"]
     qx, ql, qo = cfg["queries"]
@@ -59,6 +66,8 @@ def test_facade_reproduces_oracle(tmp_path, oracle_lib):
         assert int(tok[3]) == len(qd)
         assert int(tok[5]) == r["best"][0] and float(tok[6]) == r["best"][1]
         assert int(tok[10]) == r["n"]
+        if eigen_like:   # the node's own Eigen pose arithmetic agrees with sgtd_localization_check
+            assert tok[tok.index("eigen_check") + 1] == "1"
         cands = tok[tok.index("cands") + 1:]
         exp = [f"{c['frame']}:{c['score']}:{max(c['ninlier'], 0) if c['score'] > 0 else 0}" for c in r["cands"]]
         assert cands == exp

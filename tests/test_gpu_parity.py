@@ -291,11 +291,16 @@ def test_single_scan_facade_flow(world, oracle_lib):
 
 def test_edge_cases(oracle_lib):
     mgr = capi.STDescManager(device=0)
-    # fewer nodes than descriptor_near_num -> error status (reference: UB)
-    few = capi.make_nodes(np.random.default_rng(0).normal(size=(5, 3)), np.full(5, 5))
-    with pytest.raises(capi.SgtdError) as e:
-        mgr.build(few)
-    assert e.value.status == capi.E_TOO_FEW_NODES
+    # fewer nodes than descriptor_near_num (reference: UB) -> zero descriptors, the scan keeps its slot
+    rng0 = np.random.default_rng(0)
+    few = capi.make_nodes(rng0.normal(size=(5, 3)), np.full(5, 5))
+    assert mgr.build(few).download()[0].shape[0] == 0
+    full = capi.make_nodes(rng0.uniform(-30, 30, (40, 3)), rng0.integers(3, 12, 40))
+    mixed = np.concatenate([full, few, full[:0], full])          # scans: 40, 5, 0, 40 nodes
+    gd, goff = mgr.build(mixed, np.array([0, 40, 45, 45, 85], np.int64)).download()
+    alone, _ = mgr.build(full).download()
+    assert goff[2] == goff[1] and goff[3] == goff[2]             # the sparse and the empty scan: nothing
+    assert gd[:goff[1]].tobytes() == alone.tobytes() and gd[goff[3]:].tobytes() == alone.tobytes()
     # empty batch, empty DB search
     rng = np.random.default_rng(1)
     nodes = capi.make_nodes(rng.uniform(-30, 30, (40, 3)), rng.integers(3, 12, 40))

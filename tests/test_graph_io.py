@@ -88,25 +88,60 @@ def test_pose_error_matches_compute_adj_rpe():
 
 
 def test_localization_check_is_the_main_loops_success_test():
-    """T_est = T_map[match] * [R|t]_loop * extrinsic; success iff T < 5 m and R < 10 deg
-    (R/src/semantic_graph_localization.cpp:724-750)."""
+    """MAt = T_map[match] * [R|t]_loop * refinement  against  gt * BASE2OUSTER; success iff T < 5 m and
+    R < 10 deg (R/src/semantic_graph_localization.cpp:724-750).  The expected values are formed here with
+    numpy from the reference's expressions, not from the library."""
     rng = np.random.default_rng(9)
     n_ok = 0
     for i in range(40):
-        mp, gt, ex = _rand_pose(rng), _rand_pose(rng), _rand_pose(rng)
-        # a loop transform that reproduces gt up to a perturbation of growing size
-        want = np.linalg.inv(_T(mp)) @ _T(gt) @ np.linalg.inv(_T(ex))
+        mp, gt, ex, rf = _rand_pose(rng), _rand_pose(rng), _rand_pose(rng), _rand_pose(rng)
+        if i % 2:
+            rf = np.eye(4)[:3].reshape(12)           # GICP disabled: transformation = identity
+        # a loop transform that reproduces gt * extrinsic up to a perturbation of growing size
+        want = np.linalg.inv(_T(mp)) @ _T(gt) @ _T(ex) @ np.linalg.inv(_T(rf))
         ang = np.radians(0.5 * i)
         c, s_ = np.cos(ang), np.sin(ang)
         pert = np.array([[c, -s_, 0, 0.2 * i], [s_, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
         loop = want @ pert
-        ok, t, r, est = capi.localization_check(mp, loop[:3, :3], loop[:3, 3], gt, extr12=ex)
-        T_est = _T(mp) @ loop @ _T(ex)
-        assert np.allclose(_T(est), T_est, atol=1e-9)
-        t_ref, r_ref = capi.pose_error(gt, T_est[:3].reshape(12))
-        assert abs(t - t_ref) < 1e-9 and abs(r - r_ref) < 1e-9
-        assert ok == (t < 5.0 and r < 10.0)
+        ok, t, r, est = capi.localization_check(mp, loop[:3, :3], loop[:3, 3], gt, refine12=rf, gt_extr12=ex)
+        MAt = _T(mp) @ loop @ _T(rf)                 # transform_j1 * new_trans * transformation
+        gt_test = _T(gt) @ _T(ex)                    # transform_test * BASE2OUSTER
+        assert np.allclose(_T(est), MAt, atol=1e-9)
+        d = np.linalg.inv(MAt) @ gt_test             # compute_adj_rpe(gt = transform_test, lo = MAt)
+        t_ref = np.linalg.norm(d[:3, 3])
+        r_ref = abs(np.degrees(np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1))))
+        assert abs(t - t_ref) < 1e-8 and abs(r - r_ref) < 1e-5      # acos is ill-conditioned at 0 deg
+        assert ok == (t_ref < 5.0 and r_ref < 10.0)
         n_ok += ok
     assert 0 < n_ok < 40                        # both outcomes were exercised
-    ok, t, r, _ = capi.localization_check(mp, np.eye(3), np.zeros(3), mp)   # no extrinsic, exact pose
+    # an extrinsic on the ground-truth side is NOT the same as one on the estimate
+    ok1, t1, _, _ = capi.localization_check(mp, np.eye(3), np.zeros(3), mp, gt_extr12=ex)
+    ok2, t2, _, _ = capi.localization_check(mp, np.eye(3), np.zeros(3), mp, refine12=ex)
+    assert t1 > 1.0 and abs(t1 - t2) < 1e-6     # same distance here, but from opposite sides: est*E vs gt*E
+    ok, t, r, _ = capi.localization_check(mp, np.eye(3), np.zeros(3), mp)   # nothing extra, exact pose
     assert ok and t < 1e-9 and r < 1e-5
+
+
+def test_recall_rank_is_the_main_loops_bookkeeping():
+    """sort by fitness descending, first candidate within 10 m of the ground truth -> its position
+    (R/src/semantic_graph_localization.cpp:603-646)."""
+    rng = np.random.default_rng(10)
+    n_map = 30
+    mp = np.stack([_rand_pose(rng) for _ in range(n_map)])
+    for it in range(30):
+        nc = int(rng.integers(0, 12))
+        c = np.zeros(nc, capi.CAND_DTYPE)
+        c["frame"] = rng.choice(n_map, nc, replace=False)
+        c["score"] = rng.integers(-1, 6, nc)
+        gt = mp[int(rng.integers(n_map))].copy()
+        gt[[3, 7, 11]] += rng.normal(0, 4, 3)
+        rank, order = capi.recall_rank(c, mp, gt)
+        want_order = sorted(range(nc), key=lambda i: (-int(c["score"][i]), i))
+        assert list(order) == want_order
+        want = -1
+        for pos, i in enumerate(want_order):
+            t, _ = capi.pose_error(gt, mp[c["frame"][i]])
+            if t < 10.0:
+                want = pos
+                break
+        assert rank == want
