@@ -128,10 +128,14 @@ typedef struct sgtd_loop_result {
   double score;
 } sgtd_loop_result;
 
-/* Work counters of the vote kernel (for the roofline's algorithmic bytes:
- * bytes = 32*Q + 16*P + 28*E + 12*M). */
+/* Work counters of the vote stage.  Q query descriptors, P probes that pass the 1.5-ball
+ * test, Pfound those that hit a bucket, E bucket entries tested (summed per probe), M matches
+ * (= votes cast).  B / Eu (only with option "stats_unique", else 0): distinct buckets probed
+ * by the batch and the entries they hold -- the part of the index any formulation must read
+ * at least once.  Roofline bytes: per-probe model 32*Q + 16*P + 28*E + 12*M (SURVEY.md 8d,
+ * what the streaming kernel moves); one-pass bound of the join 16*Eu + 32*Q + 16*P + 4*nq*F. */
 typedef struct sgtd_vote_stats {
-  int64_t Q, P, Pfound, E, M;
+  int64_t Q, P, Pfound, E, M, B, Eu;
 } sgtd_vote_stats;
 
 /* Per-stage device times of the last sgtd_search, milliseconds (CUDA events on
@@ -163,6 +167,14 @@ int64_t sgtd_db_size(const sgtd_handle *h);           /* descriptors on this ran
 void *sgtd_stream(const sgtd_handle *h);              /* cudaStream_t of the handle */
 int sgtd_synchronize(sgtd_handle *h);
 int64_t sgtd_kernel_launches(const sgtd_handle *h);   /* kernels launched so far */
+/* Behaviour switches for experiments and parity tests.  They never change results, only which
+ * kernel formulation runs: "vote_stream" (1 = the per-probe streaming vote kernel, exact FP64 on every
+ * entry, instead of the bucket-major join), "join_groups" (query groups of the join, 0 = automatic),
+ * "collect_mode" (0 auto, 1 inverted, 2 per-descriptor), "collect_group", "debug_novote".  The same
+ * switches are read once from the environment by sgtd_create (SGTD_VOTE_MODE=stream, SGTD_JOIN_GROUPS,
+ * SGTD_COLLECT_MODE=desc|inv, SGTD_COLLECT_GROUP, SGTD_DEBUG_NOVOTE); sgtd_search never reads the
+ * environment. */
+int sgtd_set_option(sgtd_handle *h, const char *name, int32_t value);
 
 /* ---- stage 2: triangle descriptors --------------------------------------- */
 /* nodes of scan s are nodes[scan_offsets[s] .. scan_offsets[s+1]).  frame_ids

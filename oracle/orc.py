@@ -63,6 +63,8 @@ def lib():
         L.orc_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
         L.orc_add.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_db_key.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_build_add_many.restype = C.c_int64
+        L.orc_build_add_many.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.orc_search.restype = C.c_int32
         L.orc_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
@@ -126,6 +128,14 @@ class Oracle:
     def add(self, descs):
         descs = np.ascontiguousarray(descs, dtype=DESC_DTYPE)
         lib().orc_add(self._h, _p(descs), descs.shape[0])
+
+    def build_add_many(self, xyz, label, off, nthreads=None):
+        """map phase for many keyframes: build (parallel) + add (in order); same DB as per-frame calls"""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        label = np.ascontiguousarray(label, dtype=np.uint32)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        return lib().orc_build_add_many(self._h, _p(xyz), _p(label), _p(off), off.shape[0] - 1,
+                                        nthreads or os.cpu_count() or 1)
 
     @staticmethod
     def db_keys(descs):

@@ -397,6 +397,35 @@ void orc_add(orc_handle *h, const orc_desc *d, int64_t n) {
   }
 }
 
+/* The map phase of the node (R/src/semantic_graph_localization.cpp:455-458) for many keyframes:
+ * BuildSingleScanSTD of every scan (independent: done on `nthreads` threads, each scan stamped with the
+ * frame id it will be added as), then AddSTDescs in scan order.  A scan with fewer nodes than
+ * descriptor_near_num is added as an empty keyframe.  Returns the number of descriptors added. */
+int64_t orc_build_add_many(orc_handle *h, const float *xyz, const uint32_t *label, const int64_t *off,
+                           int32_t nscans, int32_t nthreads) {
+  std::vector<std::vector<orc_desc>> per((size_t)nscans);
+  const uint32_t base = h->current_frame_id;
+  const int npairs = (h->cfg.descriptor_near_num - 1) * (h->cfg.descriptor_near_num - 2) / 2;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int32_t s = 0; s < nscans; ++s) {
+    orc_handle tmp;
+    tmp.cfg = h->cfg;
+    tmp.current_frame_id = base + (uint32_t)s;
+    const int32_t K = (int32_t)(off[s + 1] - off[s]);
+    std::vector<orc_desc> &v = per[(size_t)s];
+    v.resize((size_t)std::max(K, 1) * npairs);
+    const int64_t n = orc_build(&tmp, xyz + 3 * off[s], label + off[s], K, v.data(), (int64_t)v.size());
+    v.resize((size_t)std::max<int64_t>(n, 0));
+  }
+  int64_t total = 0;
+  for (int32_t s = 0; s < nscans; ++s) {
+    orc_add(h, per[(size_t)s].data(), (int64_t)per[(size_t)s].size());
+    total += (int64_t)per[(size_t)s].size();
+    std::vector<orc_desc>().swap(per[(size_t)s]);
+  }
+  return total;
+}
+
 /* SearchLoop, R/src/STDesc.cpp:84-147 */
 int32_t orc_search(orc_handle *h, const orc_desc *q, int64_t nq, orc_cand *cands,
                    int32_t cap_cand, int32_t *m_q, uint8_t *m_cell, uint32_t *m_g,
@@ -448,10 +477,13 @@ int32_t orc_search(orc_handle *h, const orc_desc *q, int64_t nq, orc_cand *cands
   const int64_t F = (int64_t)h->current_frame_id;
   std::vector<int32_t> votes((size_t)std::max<int64_t>(F, 1), 0);
   std::vector<Match> all;
+  std::vector<int32_t> match_index_vec; /* frame id of every match, as the reference keeps it (:415-417) */
   for (int64_t i = 0; i < nq; ++i)
     for (const Match &m : per_q[i]) {
-      votes[h->db[m.g].frame] += 1;
+      const int32_t f = (int32_t)h->db[m.g].frame;
+      votes[f] += 1;
       all.push_back(m);
+      match_index_vec.push_back(f);
     }
   if (stats) { stats->Q = nq; stats->P = sP; stats->Pfound = sPf; stats->E = sE; stats->M = (int64_t)all.size(); }
   if (votes_out)
@@ -470,8 +502,9 @@ int32_t orc_search(orc_handle *h, const orc_desc *q, int64_t nq, orc_cand *cands
     std::memset(&cd, 0, sizeof(cd));
     cd.frame = max_idx; cd.votes = max_vote; cd.match_off = (int32_t)moff;
     int32_t nm = 0;
-    for (const Match &m : all)
-      if ((int32_t)h->db[m.g].frame == max_idx) {
+    for (size_t mi = 0; mi < all.size(); ++mi)
+      if (match_index_vec[mi] == max_idx) { /* :437-447 */
+        const Match &m = all[mi];
         if (moff + nm >= cap_match) return -2;
         m_q[moff + nm] = m.q; m_cell[moff + nm] = m.cell; m_g[moff + nm] = m.g;
         ++nm;

@@ -97,6 +97,11 @@ int64_t orc_build(orc_handle *h, const float *xyz, const uint32_t *label,
 /* AddSTDescs (R/src/STDesc.cpp:149-172). */
 void orc_add(orc_handle *h, const orc_desc *d, int64_t n);
 
+/* Build + add of many keyframes at once (scan s = nodes off[s]..off[s+1]); builds run on nthreads
+ * threads, adds in scan order.  Same database as nscans orc_build / orc_add calls. */
+int64_t orc_build_add_many(orc_handle *h, const float *xyz, const uint32_t *label, const int64_t *off,
+                           int32_t nscans, int32_t nthreads);
+
 /* DB key of a descriptor as AddSTDescs forms it; returns x,y,z,code. */
 void orc_db_key(const orc_desc *d, int32_t out[4]);
 

@@ -42,7 +42,7 @@ class Config(C.Structure):
 
 
 class VoteStats(C.Structure):
-    _fields_ = [(k, C.c_int64) for k in ("Q", "P", "Pfound", "E", "M")]
+    _fields_ = [(k, C.c_int64) for k in ("Q", "P", "Pfound", "E", "M", "B", "Eu")]
 
 
 class Timings(C.Structure):
@@ -96,6 +96,7 @@ SYMBOLS = {
     "sgtd_scan_read_kitti": (C.c_int, [C.c_char_p, C.c_char_p, _VP, _VP, _I64, _VP]),
     "sgtd_pose_error": (C.c_int, [_VP, _VP, _VP, _VP]),
     "sgtd_localization_check": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP]),
+    "sgtd_set_option": (C.c_int, [_VP, C.c_char_p, C.c_int32]),
     "sgtd_recall_rank": (C.c_int, [_VP, C.c_int32, _VP, C.c_int64, _VP, C.c_double, _VP, _VP]),
 }
 
@@ -235,7 +236,7 @@ class SearchResult:
     def stats(self):
         s, t = VoteStats(), Timings()
         self.mgr._chk(lib().sgtd_result_stats(self.mgr._h, self.ptr, C.byref(s), C.byref(t)))
-        return ({k: getattr(s, k) for k in ("Q", "P", "Pfound", "E", "M")},
+        return ({k: getattr(s, k) for k in ("Q", "P", "Pfound", "E", "M")} | ({"B": s.B, "Eu": s.Eu} if s.B else {}),
                 {k: getattr(t, k) for k, _ in Timings._fields_})
 
     def free(self):
@@ -292,6 +293,10 @@ class STDescManager:
     @property
     def stream(self):
         return int(lib().sgtd_stream(self._h) or 0)
+
+    def set_option(self, name, value):
+        """experiment / parity switches (sgtd_set_option): vote_stream, join_groups, collect_mode, ..."""
+        self._chk(lib().sgtd_set_option(self._h, name.encode(), int(value)))
 
     def shard_init(self, rank, nranks, frames_per_rank, unique_id=None):
         self._chk(lib().sgtd_shard_init(self._h, rank, nranks, frames_per_rank, _p(unique_id)))

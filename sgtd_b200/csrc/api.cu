@@ -211,7 +211,32 @@ int sgtd_create(const sgtd_config *cfg, int device, sgtd_handle **out) {
   }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+  // experiment switches: the environment is read here, once, never inside sgtd_search
+  if (const char *v = getenv("SGTD_VOTE_MODE")) h->opt.vote_stream = strcmp(v, "stream") == 0;
+  if (const char *v = getenv("SGTD_JOIN_GROUPS")) h->opt.join_groups = std::max(0, atoi(v));
+  if (const char *v = getenv("SGTD_COLLECT_MODE")) h->opt.collect_mode = strcmp(v, "desc") == 0 ? 2 : 1;
+  if (const char *v = getenv("SGTD_COLLECT_GROUP")) h->opt.collect_group = std::max(0, atoi(v));
+  if (getenv("SGTD_DEBUG_NOVOTE")) h->opt.debug_novote = 1;
+  if (const char *v = getenv("SGTD_JOIN_IMPL")) h->opt.join_impl = (atoi(v) >= 0 && atoi(v) <= 2) ? atoi(v) : 1;
   *out = h;
+  return SGTD_OK;
+}
+
+int sgtd_set_option(sgtd_handle *h, const char *name, int32_t value) {
+  if (!h || !name) return SGTD_E_INVALID;
+  if (!strcmp(name, "vote_stream")) h->opt.vote_stream = value != 0;
+  else if (!strcmp(name, "join_groups")) h->opt.join_groups = std::max(0, (int)value);
+  else if (!strcmp(name, "collect_mode")) h->opt.collect_mode = (value >= 0 && value <= 2) ? value : 0;
+  else if (!strcmp(name, "collect_group")) h->opt.collect_group = std::max(0, (int)value);
+  else if (!strcmp(name, "debug_novote")) h->opt.debug_novote = value != 0;
+  else if (!strcmp(name, "join_impl")) {
+    const int v = (value >= 0 && value <= 2) ? value : 1;
+    if ((v == 1) != (h->opt.join_impl == 1)) h->dirty = true;  // 16-byte vs 8-byte entries: the index is rebuilt
+    h->opt.join_impl = v;
+  }
+  else if (!strcmp(name, "stats_unique")) h->opt.stats_unique = value != 0;
+  else if (!strcmp(name, "s1_trace")) h->opt.s1_trace = value != 0;
+  else SGTD_FAIL(h, SGTD_E_INVALID, "unknown option");
   return SGTD_OK;
 }
 
@@ -221,8 +246,8 @@ int sgtd_destroy(sgtd_handle *h) {
   cudaStreamSynchronize(h->stream);
   if (h->nccl) nccl_api().CommDestroy((ncclComm_t)h->nccl);
   h->rec.release(); h->vert.release(); h->d_frame_off.release();
-  h->v_s0.release(); h->v_s1.release(); h->v_s2.release(); h->v_frame.release(); h->v_pack.release();
-  h->table.release(); h->f_key.release(); h->f_g.release(); h->f_side.release(); h->scratch.release(); h->stage_in.release();
+  h->v_s0.release(); h->v_s1.release(); h->v_s2.release(); h->v_frame.release(); h->v_pack.release(); h->v_pack8.release();
+  h->table.release(); h->f_key.release(); h->f_g.release(); h->f_side.release(); h->scratch.release(); h->stage_in.release(); h->uniq_bitmap.release();
   if (h->s1pool && h->s1pool_free) h->s1pool_free(h->s1pool);
   for (auto *r : h->result_pool) destroy_result(r);
   for (auto *b : h->batch_pool) destroy_batch(b);
@@ -479,9 +504,10 @@ int sgtd_result_stats(sgtd_handle *h, const sgtd_search_result *r, sgtd_vote_sta
   if (!h || !r) SGTD_FAIL(h, SGTD_E_INVALID, "bad argument");
   SetDevice sd(h->device);
   if (stats) {
-    unsigned long long c[5];
+    unsigned long long c[7];
     SGTD_CUDA(h, cudaMemcpy(c, r->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
     stats->Q = (int64_t)c[0]; stats->P = (int64_t)c[1]; stats->Pfound = (int64_t)c[2]; stats->E = (int64_t)c[3]; stats->M = (int64_t)c[4];
+    stats->B = (int64_t)c[5]; stats->Eu = (int64_t)c[6];
   }
   if (tm) *tm = r->tm;
   return SGTD_OK;

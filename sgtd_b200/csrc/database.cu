@@ -37,13 +37,25 @@ __global__ void k_make_keys(const DescRec *rec, int64_t n, uint64_t *key, uint32
 }
 
 __global__ void k_gather_index(const DescRec *rec, const uint32_t *perm, int64_t n, uint32_t frame_lo,
-                               double *s0, double *s1, double *s2, uint32_t *fr, float4 *pack) {
+                               double *s0, double *s1, double *s2, uint32_t *fr, float4 *pack, uint64_t *pack8) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   DescRec r = rec[perm[i]];
   s0[i] = r.s[0]; s1[i] = r.s[1]; s2[i] = r.s[2];
   fr[i] = r.frame - frame_lo;
-  pack[i] = make_float4((float)r.s[0], (float)r.s[1], (float)r.s[2], __uint_as_float(r.frame - frame_lo));
+  if (pack) pack[i] = make_float4((float)r.s[0], (float)r.s[1], (float)r.s[2], __uint_as_float(r.frame - frame_lo));
+  // 8-byte entry of the join: the sides relative to the bucket's cell (cell = (int)(side + 0.5), the key's
+  // x, y, z; side - cell lies in [-0.5, 0.5)) in 13-bit fixed point, and the local frame index (25 bits)
+  if (!pack8) return;
+  uint64_t w = (uint64_t)(r.frame - frame_lo) << kPack8FrameShift;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double cell = (double)__double2int_rz(__dadd_rn(r.s[k], 0.5));
+    int u = (int)floor((r.s[k] - cell + 0.5) * (double)(1 << kPack8Bits));
+    u = u < 0 ? 0 : (u > (1 << kPack8Bits) - 1 ? (1 << kPack8Bits) - 1 : u);
+    w |= (uint64_t)u << (kPack8Bits * k);
+  }
+  pack8[i] = w;
 }
 
 __global__ void k_insert_buckets(const uint64_t *ukeys, const uint32_t *offs, const uint32_t *cnts,
@@ -124,10 +136,17 @@ int finalize_db(sgtd_handle *h) {
   SGTD_LAUNCHED(h);
   SGTD_CUDA(h, h->v_s0.reserve(N, st, false)); SGTD_CUDA(h, h->v_s1.reserve(N, st, false));
   SGTD_CUDA(h, h->v_s2.reserve(N, st, false)); SGTD_CUDA(h, h->v_frame.reserve(N, st, false));
-  SGTD_CUDA(h, h->v_pack.reserve(N, st, false));
-  h->v_s0.n = h->v_s1.n = h->v_s2.n = h->v_frame.n = h->v_pack.n = (size_t)N;
+  // the default join (k_vote_join) streams 16-byte float entries; the 8-byte cell-relative entries of the
+  // experimental joins (join_impl 0 / 2) are only built on request
+  const bool want16 = h->opt.join_impl == 1, want8 = !want16;
+  if (want8 && F >= (1ll << (64 - kPack8FrameShift))) SGTD_FAIL(h, SGTD_E_CAPACITY, "more than 2^25 keyframes on one rank");
+  if (want16) SGTD_CUDA(h, h->v_pack.reserve(N, st, false));
+  if (want8) SGTD_CUDA(h, h->v_pack8.reserve((size_t)N + 4, st, false));
+  h->v_s0.n = h->v_s1.n = h->v_s2.n = h->v_frame.n = (size_t)N;
+  h->v_pack.n = want16 ? (size_t)N : 0;
+  h->v_pack8.n = want8 ? (size_t)N : 0;
   k_gather_index<<<GB, TB, 0, st>>>(h->rec.p, i1, N, (uint32_t)h->frame_lo(), h->v_s0.p, h->v_s1.p, h->v_s2.p,
-                                    h->v_frame.p, h->v_pack.p);
+                                    h->v_frame.p, want16 ? h->v_pack.p : nullptr, want8 ? h->v_pack8.p : nullptr);
   SGTD_LAUNCHED(h);
   SGTD_CUDA(h, cudaGetLastError());
   // buckets

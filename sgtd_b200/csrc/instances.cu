@@ -26,8 +26,14 @@
 // on the host with the real container fed the labels in first-appearance order.
 // Centroids are sequential float32 sums in ascending point order (get_json.cpp:266-274).
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <thread>
 #include <unordered_map>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "internal.cuh"
 
@@ -54,7 +60,10 @@ struct Task {
 struct TaskState {  // written by the device
   double minPitch, maxPitch, minPolar, maxPolar;
   int width, height, polarNum, nevents, labelCount, ndistinct;
+  int nvox, ninvis;  // occupied voxels; seed events of invisible (top pitch layer) voxels
   int64_t pool_off;
+  long long dbg_cyc[4];  // option s1_trace: cycles of the replay phases (build, translate, replay, write-back)
+  int dbg_active, dbg_windows;
 };
 
 struct S1Buffers {
@@ -66,7 +75,7 @@ struct S1Buffers {
   double *polar;     // 3 per point
   int *slot;         // voxel slot per point
   int4 *events;      // seed events in point order: (local rank, voxel slot, packed voxel coords, -)
-  int *nbr;          // 27 neighbour slots per event
+  int2 *evc;         // replay form of the events: (table slot | which << 28 | visible << 30, local rank)
   int *pt_label;     // labels of points of invisible voxels
   int *final_label;  // final label per point
   int *parent, *count, *first;  // per label value
@@ -256,123 +265,281 @@ __global__ void __launch_bounds__(kS1Threads) k_dcvc_prepare(S1Buffers B, double
     base += total;
   }
   if (tid == 0) B.ts[blockIdx.x].nevents = base;
-  __syncthreads();
-  // 4. neighbour voxel slots of every event, searchKNN order (:365-385): z (pitch) outer, y (polar),
-  //    x (azimuth) inner; -1 = skipped by the guards or no such voxel.  Parallel here, so that the
-  //    sequential replay only has to read 27 consecutive ints per event.
-  const int nev = base;
-  int *nbr = B.nbr + 27 * t.idx_off;
-  for (int w = tid; w < nev * 27; w += kS1Threads) {
-    const int e = w / 27, k = w - e * 27;
-    const int coord = B.events[t.idx_off + e].z;
-    const int az = coord & 1023, po = (coord >> 10) & 2047, pi = coord >> 21;
-    const int z = pi - 1 + k / 9, y = po - 1 + (k / 3) % 3, x = az - 1 + k % 3;
-    int nb = -1;
-    if (!(z < 0 || z > height) && !(y < 0 || y > polarNum)) {
-      int ax = x;
-      if (ax < 0) ax = width - 1;
-      if (ax > 300) ax = 300;
-      nb = table_lookup(t_key, mask, (ax * (polarNum + 1) + y) + z * (polarNum + 1) * (width + 1));
-    }
-    nbr[w] = nb;
-  }
+  // 4. voxel and invisible-seed counts (the replay picks its table class from them)
+  int nv = 0, ni = 0;
+  for (int sidx = tid; sidx < t.tab_size; sidx += kS1Threads) nv += __ldcg(&t_key[sidx]) != kEmptyVoxel;
+  for (int r = tid; r < t.npts; r += kS1Threads) ni += (__ldcg(&t_coord[B.slot[t.idx_off + r]]) >> 21) > height;
+  int tot_v, tot_i;
+  block_excl_scan(nv, s_warp, tot_v);
+  block_excl_scan(ni, s_warp, tot_i);
+  if (tid == 0) { B.ts[blockIdx.x].nvox = tot_v; B.ts[blockIdx.x].ninvis = tot_i; }
 }
 
 __device__ __forceinline__ int uf_find_ro(const int *parent, int x) {
   while (true) { const int p = __ldcg(parent + x); if (p == x) return x; x = p; }
 }
 
-// Union-find over label values: the first kUfSmem labels live in shared memory (every task of the
-// test and bench workloads fits), the rest in the task's global array.
-constexpr int kUfSmem = 8192;
-struct UnionFind {
-  int *sm, *gl;
-  __device__ __forceinline__ int get(int x) const { return x < kUfSmem ? sm[x] : __ldcg(gl + x); }
-  __device__ __forceinline__ void set(int x, int v) { if (x < kUfSmem) sm[x] = v; else gl[x] = v; }
-  __device__ __forceinline__ int find(int x) {
-    int r = x;
-    while (true) { const int p = get(r); if (p == r) break; r = p; }
-    while (x != r) { const int p = get(x); set(x, r); x = p; }  // path compression
-    return r;
+// ---- K4: replay of the seed events (DCVC, :272-355), one CTA per task -------------------------------
+// The reference's walk is sequential over the seed events, but everything INSIDE one event is parallel:
+//  * the curved-voxel table of the task lives in SHARED memory (open addressing; 4-byte word = packed
+//    (azimuth, polar, pitch) index + 2-bit state, 2-byte label), rebuilt from the global table by the whole
+//    CTA; tasks whose table does not fit use the global table (kSmem = false);
+//  * warp 0 replays.  A window of 32 consecutive events is tested at once against the current state of
+//    their own voxels: events whose point is already labelled (voxel ALL, or the other of its two seed
+//    points) are skipped 32 at a time; the first still-unlabelled seed is the active one;
+//  * for the active seed lanes 0..26 compute the 27 neighbour keys (searchKNN order, :365-385), look them
+//    up and read their states in parallel.  The sequential walk (:317-346) collapses to warp primitives:
+//    with r_k the union-find root of labelled neighbour k, `cur` only changes at the FIRST occurrence of
+//    each distinct root (later occurrences are already merged), so the roots are chained
+//    parent[r_f1] = r_f2, parent[r_f2] = r_f3, ... in first-occurrence order (the merge keeps the
+//    neighbour's value, :323-327), an unlabelled neighbour takes the root of the last first-occurrence
+//    before it, and the final `cur` is the root of the last one;
+//  * the events stream through a small shared-memory ring that is refilled one chunk ahead.
+// Results (voxel states, label forest) are written back to the global arrays k_s1_finish reads.
+constexpr int kRpThreads = 128;
+constexpr int kUfCap = 1024;     // union-find entries in shared memory; beyond: the task's global array
+constexpr int kRing = 256;       // events in the ring (two chunks of 128)
+constexpr uint32_t kVEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kCoordMask = 0x07FFFFFFu;  // az:9 | polar:10 | pitch:8
+
+__device__ __forceinline__ uint32_t coord27(int az, int po, int pi) { return (uint32_t)az | ((uint32_t)po << 9) | ((uint32_t)pi << 19); }
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) { x *= 0x9E3779B1u; return x ^ (x >> 15); }
+
+template <bool kSmem>
+struct VoxTable {
+  // shared-memory form
+  uint32_t *w; uint16_t *lab; uint32_t mask;
+  // global form (the task's own table, keyed by the reference's voxel index)
+  const int *t_key; int *t_kind, *t_label; int gmask; int polarNum, width;
+  __device__ __forceinline__ int lookup(int az, int po, int pi) const {
+    if (kSmem) {
+      // linear probing in a sparsely filled table (load <= 0.3: most searches, hits or misses, end at the
+      // first word).  The loop is kept convergent: a lane that is done idles until the slowest one is.
+      const uint32_t key = coord27(az, po, pi);
+      uint32_t pos = hash_u32(key) & mask;
+      int found = -2;  // -2: still searching
+      while (true) {
+        if (found == -2) {
+          const uint32_t v = w[pos];
+          if (v == kVEmpty) found = -1;
+          else if ((v & kCoordMask) == key) found = (int)pos;
+          else pos = (pos + 1) & mask;
+        }
+        if (!__any_sync(__activemask(), found == -2)) return found;
+      }
+    } else {
+      return table_lookup(t_key, gmask, (az * (polarNum + 1) + po) + pi * (polarNum + 1) * (width + 1));
+    }
+  }
+  __device__ __forceinline__ void get(int slot, int &kind, int &label) const {
+    if (kSmem) { kind = (int)(w[slot] >> 27) & 3; label = lab[slot]; }
+    else { kind = __ldcg(t_kind + slot); label = __ldcg(t_label + slot); }
+  }
+  __device__ __forceinline__ int kind(int slot) const { return kSmem ? (int)(w[slot] >> 27) & 3 : __ldcg(t_kind + slot); }
+  __device__ __forceinline__ void set(int slot, int kind, int label) {
+    if (kSmem) { w[slot] = (w[slot] & kCoordMask) | ((uint32_t)kind << 27); lab[slot] = (uint16_t)label; }
+    else { t_kind[slot] = kind; t_label[slot] = label; }
+  }
+  __device__ __forceinline__ void set_kind(int slot, int kind) {
+    if (kSmem) w[slot] = (w[slot] & kCoordMask) | ((uint32_t)kind << 27);
+    else t_kind[slot] = kind;
   }
 };
 
-// ---- K4: sequential replay of the seed events, one warp per task (DCVC, :272-355) ---------
-// Per event the warp reads one prefetched record + 27 precomputed neighbour slots, gathers the 27
-// voxel states in parallel, and lane 0 applies the reference's walk.
-__global__ void __launch_bounds__(32) k_dcvc_replay(S1Buffers B) {
-  __shared__ int s_nb[27], s_st[27], s_lb[27];
-  __shared__ int s_parent[kUfSmem];
+struct UnionFind2 {
+  int *sm, *gl;
+  __device__ __forceinline__ int get(int x) const { return x < kUfCap ? sm[x] : __ldcg(gl + x); }
+  __device__ __forceinline__ void set(int x, int v) { if (x < kUfCap) sm[x] = v; else gl[x] = v; }
+  // read-mostly find with path halving; concurrent callers only ever move pointers towards the root
+  __device__ __forceinline__ int find(int x) {
+    while (true) {
+      const int p = get(x);
+      if (p == x) return x;
+      const int g = get(p);
+      if (g != p) set(x, g);
+      x = g;
+    }
+  }
+};
+
+// nvox_lo < nvox <= nvox_hi selects the tasks of this launch (kSmem: table of `slots` entries in dynamic
+// shared memory); seeds that can create more labels than a 16-bit label holds go to the global form.
+template <bool kSmem>
+__global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slots, int nvox_lo, int nvox_hi) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ int s_parent[kUfCap];
+  __shared__ uint32_t s_stamp[kUfCap];  // per root: (event number << 5 | 31 - lowest lane that saw it in that event)
+  __shared__ int2 s_ring[kRing];
   const Task t = B.tasks[blockIdx.x];
   if (t.policy != P_DCVC) return;
-  const int lane = threadIdx.x;
   const TaskState ts = B.ts[blockIdx.x];
-  const int height = ts.height;
-  int *t_kind = B.t_kind + t.tab_off, *t_label = B.t_label + t.tab_off;
-  UnionFind uf{s_parent, B.parent + t.lab_off};
-  int *pt_label = B.pt_label + t.idx_off;
-  const int4 *events = B.events + t.idx_off;
-  const int *nbr = B.nbr + 27 * t.idx_off;
-  int labelCount = 0;
+  const bool fits16 = ts.nvox + ts.ninvis < 65000;
+  if (kSmem) { if (!(ts.nvox > nvox_lo && ts.nvox <= nvox_hi && fits16)) return; }
+  else if (ts.nvox <= nvox_lo && fits16) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int height = ts.height, polarNum = ts.polarNum, width = ts.width;
   const int nev = ts.nevents;
-  // software pipeline: record and neighbour row of event e+1 are in flight while e is processed
-  int4 ev_next = nev > 0 ? events[0] : make_int4(0, 0, 0, 0);
-  int nb_next = (nev > 0 && lane < 27) ? nbr[lane] : -1;
-  for (int e = 0; e < nev; ++e) {
-    const int4 ev = ev_next;
-    const int nb_cur = nb_next;
-    if (e + 1 < nev) {
-      ev_next = events[e + 1];
-      if (lane < 27) nb_next = nbr[(e + 1) * 27 + lane];
+  VoxTable<kSmem> T{};
+  T.w = reinterpret_cast<uint32_t *>(s_dyn); T.lab = reinterpret_cast<uint16_t *>(s_dyn + (size_t)slots * 4); T.mask = (uint32_t)slots - 1;
+  T.t_key = B.t_key + t.tab_off; T.t_kind = B.t_kind + t.tab_off; T.t_label = B.t_label + t.tab_off; T.gmask = t.tab_size - 1;
+  T.polarNum = polarNum; T.width = width;
+  const int *g_coord = B.t_coord + t.tab_off;
+  int4 *events = B.events + t.idx_off;
+  int2 *evc = B.evc + t.idx_off;
+  int *pt_label = B.pt_label + t.idx_off;
+  const long long c0 = clock64();
+  // ---- 1. the task's table in shared memory: one insert per voxel, from the event of its lowest point
+  //         (event coord packs az | polar << 10 | pitch << 21)
+  if (kSmem) {
+    for (int i = tid; i < slots; i += kRpThreads) { T.w[i] = kVEmpty; T.lab[i] = 0; }
+    __syncthreads();
+#pragma unroll 4
+    for (int e = tid; e < nev; e += kRpThreads) {
+      const int4 ev = events[e];
+      if (!(ev.w & 1)) continue;
+      const int c = ev.z;
+      const uint32_t key = coord27(c & 1023, (c >> 10) & 2047, c >> 21);  // kind NONE = 0 in bits 27..28
+      uint32_t pos = hash_u32(key) & T.mask;
+      while (atomicCAS(&T.w[pos], kVEmpty, key) != kVEmpty) pos = (pos + 1) & T.mask;
     }
-    const int r = ev.x, v = ev.y;
-    const bool vis = (ev.z >> 21) <= height;
-    // one round trip per event: the 27 neighbour states (a visible voxel is its own neighbour 13)
-    const int st_cur = (lane < 27 && nb_cur >= 0) ? __ldcg(t_kind + nb_cur) : K_NONE;
-    const int lb_cur = (lane < 27 && nb_cur >= 0) ? __ldcg(t_label + nb_cur) : -1;
-    if (vis) {  // is the point still unlabelled?  (ev.w: bit0 = lowest point of its voxel, bit1 = second lowest)
-      const int kd = __shfl_sync(0xffffffffu, st_cur, 13);
-      if (kd == K_ALL) continue;
-      if (kd == K_NONE && !(ev.w & 1)) continue;
-      if (kd == K_HEAD && !(ev.w & 2)) continue;
-    }
-    if (lane < 27) { s_nb[lane] = nb_cur; s_st[lane] = st_cur; s_lb[lane] = lb_cur; }
-    __syncwarp();
-    if (lane == 0) {
-      int cur = -1;
-      bool self_all = false;
-      for (int k = 0; k < 27; ++k) {
-        const int nb = s_nb[k];
-        if (nb < 0) continue;
-        const int st = s_st[k];
-        if (st == K_NONE) {
-          if (cur != -1) { t_kind[nb] = K_ALL; t_label[nb] = cur; if (nb == v) self_all = true; }
-        } else {
-          const int lab = uf.find(s_lb[k]);
-          if (cur == -1) cur = lab;
-          else if (cur != lab) { uf.set(cur, lab); cur = lab; }  // relabel sweep cur -> neigh (:323-327)
-          if (st == K_HEAD) t_kind[nb] = K_ALL;
-          if (nb == v) self_all = true;
+    __syncthreads();
+  }
+  const long long c1 = clock64();
+  for (int i = tid; i < kUfCap; i += kRpThreads) s_stamp[i] = 0;
+  // ---- 2. replay form of the events: the slot of the seed's own voxel in the table that is replayed
+#pragma unroll 4
+  for (int e = tid; e < nev; e += kRpThreads) {
+    const int4 ev = events[e];
+    const int c = ev.z;
+    const int slot = kSmem ? T.lookup(c & 1023, (c >> 10) & 2047, c >> 21) : ev.y;
+    const int vis = (c >> 21) <= height;
+    evc[e] = make_int2(slot | (ev.w << 28) | (vis << 30), ev.x);
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- 3. sequential replay by warp 0
+  const long long c2 = clock64();
+  int labelCount = 0, n_active = 0, n_windows = 0;
+  if (tid < 32) {
+    UnionFind2 uf{s_parent, B.parent + t.lab_off};
+    int loaded = 0, pre_base = 0;
+    int2 pre[4];
+    auto prefetch = [&](int base) {
+      pre_base = base;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const int i = base + 32 * j + lane; pre[j] = i < nev ? evc[i] : make_int2(0, 0); }
+    };
+    auto commit = [&]() {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s_ring[(pre_base + 32 * j + lane) & (kRing - 1)] = pre[j];
+      loaded = min(nev, pre_base + 128);
+      __syncwarp();
+    };
+    prefetch(0); commit(); prefetch(128);
+    int e0 = 0;
+    while (e0 < nev) {
+      if (e0 + 32 > loaded && loaded < nev) { commit(); prefetch(loaded); }
+      // ---- window: which of the next 32 seeds is still unlabelled?
+      const int ei = e0 + lane;
+      const bool valid = ei < nev;
+      const int2 ew = valid ? s_ring[ei & (kRing - 1)] : make_int2(0, 0);
+      const int oslot = ew.x & 0x0FFFFFFF, which = (ew.x >> 28) & 3, ovis = (ew.x >> 30) & 1;
+      bool skip = !valid;
+      if (valid && ovis) {  // (which: bit0 = lowest point of its voxel, bit1 = second lowest)
+        const int kd = T.kind(oslot);
+        skip = kd == K_ALL || (kd == K_NONE && !(which & 1)) || (kd == K_HEAD && !(which & 2));
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, !skip);
+      ++n_windows;
+      if (act == 0) { e0 += 32; continue; }
+      ++n_active;
+      const int a = __ffs(act) - 1;
+      e0 += a + 1;
+      const int v = __shfl_sync(0xffffffffu, oslot, a), vis = __shfl_sync(0xffffffffu, ovis, a);
+      const int r = __shfl_sync(0xffffffffu, ew.y, a);
+      // ---- the active seed: its 27 neighbour voxels (a visible voxel is its own neighbour 13)
+      int az, po, pi;
+      if (kSmem) { const uint32_t c = T.w[v] & kCoordMask; az = c & 511; po = (c >> 9) & 1023; pi = c >> 19; }
+      else { const int c = __ldcg(g_coord + v); az = c & 1023; po = (c >> 10) & 2047; pi = c >> 21; }
+      int nb = -1, kd = K_NONE, lb = -1;
+      if (lane < 27) {
+        const int z = pi - 1 + lane / 9, y = po - 1 + (lane / 3) % 3, x = az - 1 + lane % 3;
+        if (!(z < 0 || z > height) && !(y < 0 || y > polarNum)) {
+          int ax = x;
+          if (ax < 0) ax = width - 1;
+          if (ax > 300) ax = 300;
+          if (y < polarNum) nb = T.lookup(ax, y, z);  // polar index polarNum is legal for the guard but never occupied
+        }
+        if (nb >= 0) T.get(nb, kd, lb);
+      }
+      const bool labelled = nb >= 0 && kd != K_NONE;
+      const unsigned Lm = __ballot_sync(0xffffffffu, labelled);
+
+      int root = -1;
+      if (labelled) root = uf.find(lb);
+      __syncwarp();
+      // first occurrence of each distinct root among the labelled lanes: the lowest lane wins a max-stamp
+      // (stamps of earlier events are smaller); roots beyond the shared-memory range use the match instruction
+      bool is_first = false;
+      if (__any_sync(0xffffffffu, labelled && root >= kUfCap)) {
+        unsigned grp = 0;
+        if (labelled) grp = __match_any_sync(Lm, root);
+        is_first = labelled && lane == __ffs(grp) - 1;
+      } else {
+        const uint32_t mine = ((uint32_t)n_active << 5) | (uint32_t)(31 - lane);
+        if (labelled) atomicMax(&s_stamp[root], mine);
+        __syncwarp();
+        is_first = labelled && s_stamp[root] == mine;
+      }
+      const unsigned Fm = __ballot_sync(0xffffffffu, is_first);
+      if (Fm == 0) {  // no labelled neighbour: new label for the seed and every neighbour (:340-346)
+        const int L = ++labelCount;
+        if (lane == 0) { uf.set(L, L); if (!vis) pt_label[r] = L; }
+        if (nb >= 0) T.set(nb, K_ALL, L);
+      } else {
+        // chain the distinct roots in first-occurrence order: cur -> neigh (:323-327)
+        const unsigned after = Fm & ~((2u << lane) - 1u);
+        const int nroot = __shfl_sync(0xffffffffu, root, after ? __ffs(after) - 1 : lane);
+        if (is_first && after) uf.set(root, nroot);
+        const int cur = __shfl_sync(0xffffffffu, root, 31 - __clz(Fm));
+        // an unlabelled neighbour takes the value `cur` has when the walk reaches it
+        const unsigned before = Fm & ((1u << lane) - 1u);
+        const int cprev = __shfl_sync(0xffffffffu, root, before ? 31 - __clz(before) : lane);
+        const bool takes = nb >= 0 && kd == K_NONE && before;
+        if (takes) T.set(nb, K_ALL, cprev);
+        if (labelled && kd == K_HEAD) T.set_kind(nb, K_ALL);
+        if (vis) {
+          const unsigned self = __ballot_sync(0xffffffffu, nb == v && (takes || labelled));
+          // own voxel passed while cur == -1: only the seed point itself is labelled (:330-331)
+          if (!self && lane == 0) T.set(v, K_HEAD, cur);
+        } else if (lane == 0) {
+          pt_label[r] = cur;
         }
       }
-      if (cur == -1) {  // new label for the seed and every neighbour (:340-346)
-        const int L = ++labelCount;
-        uf.set(L, L);
-        for (int k = 0; k < 27; ++k) { const int nb = s_nb[k]; if (nb >= 0) { t_kind[nb] = K_ALL; t_label[nb] = L; } }
-        if (!vis) pt_label[r] = L;
-      } else if (vis) {
-        if (!self_all) { t_kind[v] = K_HEAD; t_label[v] = cur; }  // own voxel was passed while cur == -1
-      } else {
-        pt_label[r] = cur;
-      }
+      __syncwarp();
     }
-    __syncwarp();
+    // publish the shared-memory part of the label forest for k_s1_finish
+    for (int i = 1 + lane; i <= labelCount && i < kUfCap; i += 32) uf.gl[i] = s_parent[i];
+    if (lane == 0) { B.ts[blockIdx.x].labelCount = labelCount; B.ts[blockIdx.x].dbg_active = n_active; B.ts[blockIdx.x].dbg_windows = n_windows; }
   }
-  // publish the shared-memory part of the union-find for k_s1_finish
-  __syncwarp();
-  labelCount = __shfl_sync(0xffffffffu, labelCount, 0);  // only lane 0 counted
-  for (int i = 1 + lane; i <= labelCount && i < kUfSmem; i += 32) uf.gl[i] = s_parent[i];
-  if (lane == 0) B.ts[blockIdx.x].labelCount = labelCount;
+  __syncthreads();
+  const long long c3 = clock64();
+  // ---- 4. voxel states back to the global table (one write per voxel, through its lowest point's event)
+  if (kSmem) {
+#pragma unroll 4
+    for (int e = tid; e < nev; e += kRpThreads) {
+      const int4 ev = events[e];
+      if (!(ev.w & 1)) continue;
+      const int slot = evc[e].x & 0x0FFFFFFF;
+      int kd, lb;
+      T.get(slot, kd, lb);
+      T.t_kind[ev.y] = kd; T.t_label[ev.y] = kd == K_NONE ? -1 : lb;
+    }
+  }
+  if (tid == 0) {
+    long long *d = B.ts[blockIdx.x].dbg_cyc;
+    d[0] = c1 - c0; d[1] = c2 - c1; d[2] = c3 - c2; d[3] = clock64() - c3;
+  }
 }
 
 // ---- K5: final label per point, per-label size and first point, compact label list -------
@@ -438,45 +605,60 @@ struct InstRec {  // one per instance, host-planned
 };
 
 // ---- K6: label -> instance id, per point membership ------------------------------------------
-__global__ void k_s1_scatter_map(S1Buffers B, const InstRec *inst, int ninst, int *inst_of_label) {
+__global__ void k_s1_scatter_map(S1Buffers B, const InstRec *inst, int ninst, int *inst_of_label, int *node_inst_of_label) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ninst) return;
   const Task t = B.tasks[inst[i].task];
   inst_of_label[t.lab_off + inst[i].label] = inst[i].inst_id;
+  if (inst[i].node_slot >= 0) node_inst_of_label[t.lab_off + inst[i].label] = i;  // index into inst[]
 }
-__global__ void __launch_bounds__(kS1Threads) k_s1_assign(S1Buffers B, const int *inst_of_label, int32_t *point_instance) {
+// membership of every point, and (key, position) pairs for the centroid pass: key = index of the point's
+// node instance (or all-ones), position = index of the point in the batch.  A stable sort by key then
+// lists every node instance's points contiguously in ascending point order.
+__global__ void __launch_bounds__(kS1Threads) k_s1_assign(S1Buffers B, const int *inst_of_label, const int *node_inst_of_label,
+                                                          int32_t *point_instance, uint32_t *skey, uint32_t *sval) {
   const Task t = B.tasks[blockIdx.x];
   for (int r = threadIdx.x; r < t.npts; r += kS1Threads) {
-    const int id = inst_of_label[t.lab_off + B.final_label[t.idx_off + r]];
-    if (id >= 0) point_instance[t.pt0 + B.cls_idx[t.idx_off + r]] = id;
+    const int lab = B.final_label[t.idx_off + r];
+    if (point_instance) {
+      const int id = inst_of_label[t.lab_off + lab];
+      if (id >= 0) point_instance[t.pt0 + B.cls_idx[t.idx_off + r]] = id;
+    }
+    skey[t.idx_off + r] = (uint32_t)node_inst_of_label[t.lab_off + lab];  // -1 -> 0xFFFFFFFF sorts last
+    sval[t.idx_off + r] = (uint32_t)(t.pt0 + B.cls_idx[t.idx_off + r]);
   }
 }
 
 // ---- K7: centroid = sequential float32 sum in ascending point order (get_json.cpp:266-274) ----
-// One warp per instance: 32 class points are fetched per trip (coalesced), the lanes that belong to
-// the instance are then added in lane order, so the rounding sequence is the reference's.
-__global__ void __launch_bounds__(128) k_s1_centroid(S1Buffers B, const InstRec *inst, int ninst, sgtd_node *nodes) {
+// One warp per node instance over ITS points only (contiguous in the instance-sorted position list):
+// 32 points are fetched per trip (coalesced list, gathered coordinates) and added in lane order, so the
+// rounding sequence is the reference's.
+__global__ void __launch_bounds__(128) k_s1_centroid(S1Buffers B, const InstRec *inst, int ninst, const uint32_t *sorted_pos,
+                                                     const int64_t *seg_off, sgtd_node *nodes) {
   const int i = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= ninst) return;
   const InstRec ir = inst[i];
   if (ir.node_slot < 0) return;
-  const Task t = B.tasks[ir.task];
+  const int64_t s0 = seg_off[i], n = seg_off[i + 1] - s0;
   float cx = 0.f, cy = 0.f, cz = 0.f;
-  int n = 0;
-  for (int r0 = 0; r0 < t.npts; r0 += 32) {
-    const int r = r0 + lane;
-    const bool mine = r < t.npts && B.final_label[t.idx_off + r] == ir.label;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mine) p = B.pts[t.pt0 + B.cls_idx[t.idx_off + r]];
-    unsigned m = __ballot_sync(0xffffffffu, mine);
-    n += __popc(m);
-    while (m) {
-      const int l = __ffs(m) - 1;
-      m &= m - 1;
-      cx = __fadd_rn(cx, __shfl_sync(0xffffffffu, p.x, l));
-      cy = __fadd_rn(cy, __shfl_sync(0xffffffffu, p.y, l));
-      cz = __fadd_rn(cz, __shfl_sync(0xffffffffu, p.z, l));
+  constexpr int kDepth = 4;  // 128 points in flight per trip: the two dependent loads are issued for all of them first
+  for (int64_t j0 = 0; j0 < n; j0 += 32 * kDepth) {
+    float4 p[kDepth];
+#pragma unroll
+    for (int u = 0; u < kDepth; ++u) {
+      const int64_t j = j0 + 32 * u + lane;
+      p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < n) p[u] = B.pts[sorted_pos[s0 + j]];
+    }
+#pragma unroll
+    for (int u = 0; u < kDepth; ++u) {
+      const int m = (int)max((int64_t)0, min((int64_t)32, n - j0 - 32 * u));
+      for (int l = 0; l < m; ++l) {
+        cx = __fadd_rn(cx, __shfl_sync(0xffffffffu, p[u].x, l));
+        cy = __fadd_rn(cy, __shfl_sync(0xffffffffu, p[u].y, l));
+        cz = __fadd_rn(cz, __shfl_sync(0xffffffffu, p[u].z, l));
+      }
     }
   }
   if (lane == 0) {
@@ -505,11 +687,15 @@ struct S1Pool {
   DevBuf<int64_t> d_off; DevBuf<uint32_t> d_cnt; DevBuf<Task> d_tasks; DevBuf<TaskState> d_ts;
   DevBuf<int> d_pp, d_tab, d_lab, d_pool, d_map; DevBuf<double> d_polar, d_bounds; DevBuf<unsigned long long> d_cur;
   DevBuf<InstRec> d_inst; DevBuf<sgtd_node> d_nodes;
+  DevBuf<int> d_map2; DevBuf<uint32_t> d_sort; DevBuf<int64_t> d_seg; DevBuf<unsigned char> d_cub;
   DevBuf<float4> in_pts; DevBuf<uint32_t> in_lab; DevBuf<int32_t> out_pi;  // staging of host inputs / outputs
+  cudaStream_t side[4] = {}; cudaEvent_t ev[5] = {}; bool have_streams = false;  // concurrent replay classes
   ~S1Pool() {
+    if (have_streams) { for (auto x : side) cudaStreamDestroy(x); for (auto x : ev) cudaEventDestroy(x); }
     d_off.release(); d_cnt.release(); d_tasks.release(); d_ts.release(); d_pp.release(); d_tab.release(); d_lab.release();
     d_pool.release(); d_map.release(); d_polar.release(); d_bounds.release(); d_cur.release(); d_inst.release();
     d_nodes.release(); in_pts.release(); in_lab.release(); out_pi.release();
+    d_map2.release(); d_sort.release(); d_seg.release(); d_cub.release();
   }
 };
 static void s1_pool_free(void *p) { delete static_cast<S1Pool *>(p); }
@@ -528,6 +714,14 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
   const int nscans = (int)off.size() - 1;
   const int64_t total_pts = off[nscans] - off[0];
   int rc = SGTD_OK;
+  // option s1_trace: wall-clock checkpoints of the host driver on stderr (experiments)
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto trace = [&](const char *what) {
+    if (!h->opt.s1_trace) return;
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[s1] %-28s %8.3f ms\n", what,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+  };
   node_off.assign(nscans + 1, 0);
   n_instances.assign(nscans, 0);
   nodes_out.clear();
@@ -540,11 +734,14 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
   DevBuf<int> &d_pp = sp.d_pp, &d_tab = sp.d_tab, &d_lab = sp.d_lab, &d_pool = sp.d_pool, &d_map = sp.d_map;
   DevBuf<double> &d_polar = sp.d_polar, &d_bounds = sp.d_bounds; DevBuf<unsigned long long> &d_cur = sp.d_cur;
   DevBuf<InstRec> &d_inst = sp.d_inst; DevBuf<sgtd_node> &d_nodes = sp.d_nodes;
+  DevBuf<int> &d_map2 = sp.d_map2; DevBuf<uint32_t> &d_sort = sp.d_sort; DevBuf<int64_t> &d_seg = sp.d_seg;
+  DevBuf<unsigned char> &d_cub = sp.d_cub;
   std::vector<uint32_t> hc((size_t)nscans * kMaxClass * 2 + 1);
   std::vector<Task> tasks;
   std::vector<TaskState> ts;
   std::vector<int> pool;
   std::vector<InstRec> inst;
+  std::vector<int64_t> seg;  // per instance: start of its points in the instance-sorted position list
   int64_t n_idx = 0, n_tab = 0, n_lab = 0, n_bnd = 0;
   S1Buffers B{};
   unsigned long long cursor = 0;
@@ -560,6 +757,7 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     S1_CUDA(cudaStreamSynchronize(st));
     if (hc.back()) { rc = sgtd_fail(h, SGTD_E_INVALID, "semantic label >= 32", __FILE__, __LINE__); goto done; }
   }
+  trace("histogram + sync");
   // ---- plan the (scan, class) tasks, classes ascending (gen_labels :99-227) ----
   for (int s = 0; s < nscans; ++s)
     for (int c = 0; c < kMaxClass; ++c) {
@@ -580,13 +778,14 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
       }
       tasks.push_back(t);
     }
+  trace("task plan (host)");
   if (!tasks.empty()) {
     const int nt = (int)tasks.size();
     ts.resize(nt);
     S1_CUDA(d_tasks.reserve(nt, st, false)); S1_CUDA(d_ts.reserve(nt, st, false));
     S1_CUDA(cudaMemcpyAsync(d_tasks.p, tasks.data(), nt * sizeof(Task), cudaMemcpyHostToDevice, st));
     S1_CUDA(cudaMemsetAsync(d_ts.p, 0, nt * sizeof(TaskState), st));
-    S1_CUDA(d_pp.reserve((size_t)std::max<int64_t>(n_idx, 1) * (4 + 4 + 27), st, false));  // cls_idx, slot, pt_label, final | events (int4) | nbr
+    S1_CUDA(d_pp.reserve((size_t)std::max<int64_t>(n_idx, 1) * (4 + 4 + 2), st, false));  // cls_idx, slot, pt_label, final | events (int4) | evc (int2)
     S1_CUDA(d_polar.reserve((size_t)std::max<int64_t>(n_idx, 1) * 3, st, false));
     S1_CUDA(d_tab.reserve((size_t)std::max<int64_t>(n_tab, 1) * 6, st, false));  // key,min1,min2,coord,kind,label
     S1_CUDA(d_lab.reserve((size_t)std::max<int64_t>(n_lab, 1) * 3, st, false));  // parent,count,first
@@ -597,7 +796,7 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     B.pts = d_pts; B.labels = d_labels; B.tasks = d_tasks.p; B.ts = d_ts.p;
     B.cls_idx = d_pp.p; B.slot = d_pp.p + n_idx; B.pt_label = d_pp.p + 2 * n_idx; B.final_label = d_pp.p + 3 * n_idx;
     B.events = reinterpret_cast<int4 *>(d_pp.p + 4 * n_idx);  // 4*n_idx ints = 16-byte aligned
-    B.nbr = d_pp.p + 8 * n_idx;
+    B.evc = reinterpret_cast<int2 *>(d_pp.p + 8 * n_idx);
     B.polar = d_polar.p;
     B.t_key = d_tab.p; B.t_min1 = d_tab.p + n_tab; B.t_min2 = d_tab.p + 2 * n_tab; B.t_coord = d_tab.p + 3 * n_tab;
     B.t_kind = d_tab.p + 4 * n_tab; B.t_label = d_tab.p + 5 * n_tab;
@@ -613,11 +812,37 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     k_fill_i32<<<1024, 256, 0, st>>>(B.first, n_lab, kEmptyVoxel);
     k_fill_i32<<<1024, 256, 0, st>>>(d_map.p, n_lab, -1);
     S1_CUDA(cudaMemsetAsync(d_cur.p, 0, 8, st));
+    trace("alloc + fills");
     k_s1_gather<<<nt, kS1Threads, 0, st>>>(B);
     k_dcvc_prepare<<<nt, kS1Threads, 0, st>>>(B, 0.35, 0.0004, 1.2, 1.2);  // get_json.cpp:205-208
-    k_dcvc_replay<<<nt, 32, 0, st>>>(B);
+    trace("gather + prepare");
+    {
+      // table classes of the replay: every class is launched over all tasks, a CTA leaves at once unless its
+      // task's voxel count (known on the device only) falls in the class; the last launch takes the rest
+      // with the table in global memory.  The classes run concurrently on the pool's side streams.
+      static const int kSlots[4] = {2048, 8192, 16384, 32768};
+      S1_CUDA(cudaFuncSetAttribute(k_dcvc_replay<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlots[3] * 6));
+      if (!sp.have_streams) {
+        for (auto &x : sp.side) S1_CUDA(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+        for (auto &x : sp.ev) S1_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+        sp.have_streams = true;
+      }
+      S1_CUDA(cudaEventRecord(sp.ev[0], st));
+      int lo = -1;
+      for (int c = 0; c < 4; ++c) {
+        const int hi = kSlots[c] * 3 / 10;  // load factor <= 0.3
+        cudaStream_t sc = sp.side[c];
+        S1_CUDA(cudaStreamWaitEvent(sc, sp.ev[0], 0));
+        k_dcvc_replay<true><<<nt, kRpThreads, (size_t)kSlots[c] * 6, sc>>>(B, kSlots[c], lo, hi);
+        S1_CUDA(cudaEventRecord(sp.ev[1 + c], sc));
+        lo = hi;
+      }
+      k_dcvc_replay<false><<<nt, kRpThreads, 0, st>>>(B, 0, lo, 0x7fffffff);
+      for (int c = 0; c < 4; ++c) S1_CUDA(cudaStreamWaitEvent(st, sp.ev[1 + c], 0));
+    }
+    trace("replay");
     k_s1_finish<<<nt, kS1Threads, 0, st>>>(B);
-    h->launches += 12;
+    h->launches += 16;
     S1_CUDA(cudaGetLastError());
     S1_CUDA(cudaMemcpyAsync(ts.data(), d_ts.p, nt * sizeof(TaskState), cudaMemcpyDeviceToHost, st));
     S1_CUDA(cudaMemcpyAsync(&cursor, d_cur.p, 8, cudaMemcpyDeviceToHost, st));
@@ -625,9 +850,61 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     pool.resize((size_t)cursor * 3 + 3);
     if (cursor) S1_CUDA(cudaMemcpyAsync(pool.data(), d_pool.p, (size_t)cursor * 12, cudaMemcpyDeviceToHost, st));
     S1_CUDA(cudaStreamSynchronize(st));
+    trace("finish + D2H labels");
+    if (h->opt.s1_trace) {
+      std::vector<int> ord(nt);
+      for (int i = 0; i < nt; ++i) ord[i] = i;
+      std::sort(ord.begin(), ord.end(), [&](int a, int b) { return ts[a].dbg_cyc[2] > ts[b].dbg_cyc[2]; });
+      for (int j = 0; j < std::min(nt, 6); ++j) {
+        const TaskState &x = ts[ord[j]];
+        fprintf(stderr, "[s1] task %4d cls %2d npts %6d nev %6d nvox %5d labels %5d active %5d windows %5d | kcyc build %lld transl %lld replay %lld wb %lld\n",
+                ord[j], tasks[ord[j]].cls, tasks[ord[j]].npts, x.nevents, x.nvox, x.labelCount, x.dbg_active, x.dbg_windows,
+                x.dbg_cyc[0] / 1000, x.dbg_cyc[1] / 1000, x.dbg_cyc[2] / 1000, x.dbg_cyc[3] / 1000);
+      }
+    }
     // ---- instance ids: per scan, tasks in class order; cluster order per policy ----
+    // The cluster order of a DCVC task is the iteration order of the reference's
+    // std::unordered_map<int, vector<int>> label2segIndex (labelAnalysis, :394-418), keyed by label and filled
+    // in ascending point order.  That order only depends on the key sequence, so the real container is
+    // replayed with the labels in first-appearance order (mapped type irrelevant).  Tasks are independent:
+    // they are ordered on a few host threads.
+    struct L { int label, count, first; };
+    std::vector<std::vector<L>> orders((size_t)nt);
+    auto order_task = [&](int ti) {
+      const Task &t = tasks[ti];
+      std::vector<L> ls((size_t)ts[ti].ndistinct);
+      for (int j = 0; j < ts[ti].ndistinct; ++j) {
+        const int *p = &pool[(size_t)(ts[ti].pool_off + j) * 3];
+        ls[j] = L{p[0], p[1], p[2]};
+      }
+      std::vector<L> &order = orders[(size_t)ti];
+      if (t.policy == P_DCVC) {
+        std::sort(ls.begin(), ls.end(), [](const L &a, const L &b) { return a.first < b.first; });
+        std::unordered_map<int, int> label2segIndex;  // value: position in ls
+        for (size_t j = 0; j < ls.size(); ++j) label2segIndex[ls[j].label] = (int)j;
+        for (auto &it : label2segIndex)
+          if (ls[(size_t)it.second].count >= t.minSeg) order.push_back(ls[(size_t)it.second]);
+      } else if (t.policy == P_GTINST) {
+        std::sort(ls.begin(), ls.end(), [](const L &a, const L &b) { return a.label < b.label; });
+        for (const L &l : ls) if (l.count > 20) order.push_back(l);  // get_json.cpp:146
+      } else {
+        order = ls;
+      }
+    };
+    {
+      const int nthr = std::max(1, std::min(8, (int)std::thread::hardware_concurrency()));
+      if (nthr == 1 || nt < 64) {
+        for (int ti = 0; ti < nt; ++ti) order_task(ti);
+      } else {
+        std::vector<std::thread> pool_thr;
+        std::atomic<int> next{0};
+        for (int w = 0; w < nthr; ++w)
+          pool_thr.emplace_back([&] { for (int ti = next.fetch_add(8); ti < nt; ti = next.fetch_add(8)) for (int j = ti; j < std::min(nt, ti + 8); ++j) order_task(j); });
+        for (auto &th : pool_thr) th.join();
+      }
+    }
     int cur_scan = -1, inst_id = 0;
-    int64_t node_cursor = 0;
+    int64_t node_cursor = 0, seg_cursor = 0;
     for (int ti = 0; ti < nt; ++ti) {
       const Task &t = tasks[ti];
       if (t.scan != cur_scan) {
@@ -635,28 +912,7 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
         for (int s = cur_scan + 1; s <= t.scan; ++s) node_off[s] = node_cursor;
         cur_scan = t.scan; inst_id = 0;
       }
-      struct L { int label, count, first; };
-      std::vector<L> ls((size_t)ts[ti].ndistinct);
-      for (int j = 0; j < ts[ti].ndistinct; ++j) {
-        const int *p = &pool[(size_t)(ts[ti].pool_off + j) * 3];
-        ls[j] = L{p[0], p[1], p[2]};
-      }
-      std::vector<L> order;
-      if (t.policy == P_DCVC) {
-        // labelAnalysis (:394-418): unordered_map keyed by label, filled in ascending point order,
-        // emitted in the container's iteration order.
-        std::sort(ls.begin(), ls.end(), [](const L &a, const L &b) { return a.first < b.first; });
-        std::unordered_map<int, std::vector<int>> label2segIndex;
-        std::unordered_map<int, L> info;
-        for (const L &l : ls) { label2segIndex[l.label].emplace_back(l.first); info[l.label] = l; }
-        for (auto &it : label2segIndex)
-          if (info[it.first].count >= t.minSeg) order.push_back(info[it.first]);
-      } else if (t.policy == P_GTINST) {
-        std::sort(ls.begin(), ls.end(), [](const L &a, const L &b) { return a.label < b.label; });
-        for (const L &l : ls) if (l.count > 20) order.push_back(l);  // get_json.cpp:146
-      } else {
-        order = ls;
-      }
+      const std::vector<L> &order = orders[(size_t)ti];
       const int mapped = node_map(t.cls);
       for (const L &l : order) {
         InstRec ir{};
@@ -664,24 +920,46 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
         ir.node_slot = -1; ir.node_label = 0;
         if (mapped >= 3 && mapped <= 12) { ir.node_slot = (int)node_cursor++; ir.node_label = (uint32_t)mapped; }
         inst.push_back(ir);
+        // node instances are sorted by their index in inst[]: their point lists follow each other
+        seg.push_back(seg_cursor);
+        if (ir.node_slot >= 0) seg_cursor += l.count;
       }
     }
     if (cur_scan >= 0) n_instances[cur_scan] = inst_id;
     for (int s = cur_scan + 1; s <= nscans; ++s) node_off[s] = node_cursor;
     nodes_out.resize((size_t)node_cursor);
+    trace("instance order (host)");
     if (!inst.empty()) {
       const int ni = (int)inst.size();
+      seg.push_back(seg_cursor);
       S1_CUDA(d_inst.reserve(ni, st, false));
       S1_CUDA(cudaMemcpyAsync(d_inst.p, inst.data(), ni * sizeof(InstRec), cudaMemcpyHostToDevice, st));
+      S1_CUDA(d_seg.reserve((size_t)ni + 1, st, false));
+      S1_CUDA(cudaMemcpyAsync(d_seg.p, seg.data(), ((size_t)ni + 1) * 8, cudaMemcpyHostToDevice, st));
       S1_CUDA(d_nodes.reserve((size_t)std::max<int64_t>(node_cursor, 1), st, false));
-      k_s1_scatter_map<<<(ni + 255) / 256, 256, 0, st>>>(B, d_inst.p, ni, d_map.p);
-      if (d_point_instance) k_s1_assign<<<nt, kS1Threads, 0, st>>>(B, d_map.p, d_point_instance);
-      k_s1_centroid<<<(ni + 3) / 4, 128, 0, st>>>(B, d_inst.p, ni, d_nodes.p);
-      h->launches += 3;
+      S1_CUDA(d_map2.reserve((size_t)std::max<int64_t>(n_lab, 1), st, false));
+      S1_CUDA(d_sort.reserve((size_t)std::max<int64_t>(n_idx, 1) * 4, st, false));  // key / value double buffers
+      k_fill_i32<<<1024, 256, 0, st>>>(d_map2.p, n_lab, -1);
+      k_s1_scatter_map<<<(ni + 255) / 256, 256, 0, st>>>(B, d_inst.p, ni, d_map.p, d_map2.p);
+      uint32_t *k0 = d_sort.p, *k1 = d_sort.p + n_idx, *v0 = d_sort.p + 2 * n_idx, *v1 = d_sort.p + 3 * n_idx;
+      k_s1_assign<<<nt, kS1Threads, 0, st>>>(B, d_map.p, d_map2.p, d_point_instance, k0, v0);
+      {
+        // stable LSD radix sort on the bits an instance index needs; all-ones keys (points outside node
+        // instances) end up behind every instance
+        int bits = 1;
+        while ((1ll << bits) <= ni) ++bits;
+        size_t cb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, cb, k0, k1, v0, v1, (int)n_idx, 0, bits, st);
+        S1_CUDA(d_cub.reserve(cb, st, false));
+        S1_CUDA(cub::DeviceRadixSort::SortPairs(d_cub.p, cb, k0, k1, v0, v1, (int)n_idx, 0, bits, st));
+      }
+      k_s1_centroid<<<(ni + 3) / 4, 128, 0, st>>>(B, d_inst.p, ni, v1, d_seg.p, d_nodes.p);
+      h->launches += 5;
       S1_CUDA(cudaGetLastError());
       if (node_cursor) S1_CUDA(cudaMemcpyAsync(nodes_out.data(), d_nodes.p, (size_t)node_cursor * sizeof(sgtd_node), cudaMemcpyDeviceToHost, st));
       S1_CUDA(cudaStreamSynchronize(st));
     }
+    trace("assign + centroid + D2H");
   }
   (void)total_pts;
 done:

@@ -41,6 +41,10 @@ struct __align__(16) Bucket {
   uint32_t cnt;
 };
 #define SGTD_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+// 8-byte vote-index entry: bits [0,13) [13,26) [26,39) = floor((side - cell + 0.5) * 2^13) of the three
+// sides (cell = (int)(side + 0.5) = the bucket key's x, y, z), bits [39,64) = local frame index.
+constexpr int kPack8Bits = 13;
+constexpr int kPack8FrameShift = 3 * kPack8Bits;
 
 // key = x:16 | y:16 | z:16 | code:12   (STDesc_LOC equality: x,y,z,a)
 __host__ __device__ inline uint64_t pack_key(uint32_t x, uint32_t y, uint32_t z, uint32_t code) {
@@ -122,14 +126,32 @@ struct sgtd_search_result {
   sgtd::DevBuf<uint32_t> m_q, m_g;      // match lists
   sgtd::DevBuf<uint8_t> m_cell;
   sgtd::DevBuf<int32_t> inl;            // inlier lists (same offsets as matches)
-  sgtd::DevBuf<unsigned long long> counters;  // Q,P,Pfound,E,M
+  sgtd::DevBuf<unsigned long long> counters;  // Q,P,Pfound,E,M,B,Eu
   sgtd_timings tm{};
   cudaEvent_t ev[10] = {};  // created once, reused while the object sits in the handle's pool
   bool have_ev = false;
 };
 
+// Behaviour switches of the search (experiments / parity tests).  Read ONCE, in sgtd_create, from the
+// environment (SGTD_VOTE_MODE=stream, SGTD_JOIN_GROUPS, SGTD_COLLECT_MODE=desc|inv, SGTD_COLLECT_GROUP,
+// SGTD_DEBUG_NOVOTE) and afterwards only changed through sgtd_set_option: sgtd_search never reads the
+// environment.
+struct sgtd_options {
+  int vote_stream = 0;    // 1: per-probe streaming kernel k_vote (exact FP64 everywhere) instead of the join
+  int join_groups = 0;    // 0: automatic (vote rows of a group ~ L2-resident)
+  int collect_mode = 0;   // 0: automatic, 1: inverted (k_collect_inv), 2: per-descriptor (k_collect)
+  int collect_group = 0;  // 0: all queries of the batch in one group
+  int debug_novote = 0;   // 1: run the vote kernels without casting votes (kernel timing experiments)
+  int s1_trace = 0;       // 1: stage 1 prints wall-clock checkpoints of its host driver on stderr
+  int stats_unique = 0;   // 1: also count the distinct probed buckets / their entries (sgtd_vote_stats B, Eu)
+  int join_impl = 1;      // 1 (default): k_vote_join, 16-byte float entries; experimental joins on 8-byte cell-relative
+                          // entries (index rebuilt on request): 0 = k_vote_join8 (per-lane loads), 2 = k_vote_run
+                          // (bulk-async staged tiles).  Measured on the bench workload: 9.0 / 11.4 / 12.6 ms.
+};
+
 struct sgtd_handle {
   sgtd_config cfg{};
+  sgtd_options opt{};
   sgtd::Cfg c{};
   int device = 0;
   int sm_count = 148;
@@ -150,7 +172,8 @@ struct sgtd_handle {
   bool dirty = true;
   sgtd::DevBuf<double> v_s0, v_s1, v_s2;
   sgtd::DevBuf<uint32_t> v_frame;  // LOCAL frame index of each entry
-  sgtd::DevBuf<float4> v_pack;     // {float s0, s1, s2, frame bits}: what k_vote_join streams (16 B/entry)
+  sgtd::DevBuf<float4> v_pack;     // {float s0, s1, s2, frame bits}: what the round-1 k_vote_join streams (16 B/entry; on request)
+  sgtd::DevBuf<uint64_t> v_pack8;  // cell-relative 13-bit sides + 25-bit frame: what the join streams (8 B/entry)
   sgtd::DevBuf<sgtd::Bucket> table;
   uint64_t table_mask = 0;
   int64_t n_buckets = 0;
@@ -159,6 +182,7 @@ struct sgtd_handle {
   sgtd::DevBuf<uint32_t> f_g;
   sgtd::DevBuf<double> f_side;  // side lengths in frame-view order, 3 per entry
   // scratch + recycled objects: steady-state build/search calls do no cudaMalloc/cudaFree
+  sgtd::DevBuf<uint32_t> uniq_bitmap;
   sgtd::DevBuf<unsigned char> scratch;
   sgtd::DevBuf<unsigned char> stage_in;
   std::vector<sgtd_search_result *> result_pool;

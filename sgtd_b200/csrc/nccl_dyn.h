@@ -1,8 +1,8 @@
 // nccl_dyn.h -- NCCL is bound at run time (dlopen), not at link time.
 // libsgtd_b200.so must load on hosts without NCCL (single-GPU use) and must share
 // whatever libnccl.so.2 the process already has (e.g. the newer one PyTorch bundles)
-// instead of pinning the system copy through DT_NEEDED.  Only the four entry points
-// the sharded search needs are resolved.
+// instead of pinning the system copy through DT_NEEDED.  Only the entry points the
+// sharded search needs are resolved.
 #pragma once
 #include <dlfcn.h>
 #include <nccl.h>
@@ -13,6 +13,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   bool ok = false;
 };
 inline const NcclApi &nccl_api() {
@@ -25,7 +26,8 @@ inline const NcclApi &nccl_api() {
     a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
     a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
     a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(lib, "ncclAllGather"));
-    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather;
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce;
     return a;
   }();
   return api;

@@ -83,8 +83,20 @@ struct __align__(16) QAux {
   uint32_t mask;
   uint32_t qi;
 };
+// What the bucket-run join needs per query descriptor (read once per probe of the descriptor, 48 B, the
+// whole batch ~100 MB, the descriptors of one query group L2-resident): the float sides and -thr^2
+// duplicated into f32x2 pairs (so that a 16-byte load yields aligned packed operands), the half-width of
+// the FP32 decision band, the query's frame id relative to this shard and its vote row.
+struct __align__(16) JoinDesc {
+  float s0a, s0b, s1a, s1b;     // (s0, s0), (s1, s1)
+  float s2a, s2b, nta, ntb;     // (s2, s2), (-thr^2, -thr^2)
+  uint32_t wband, qframe, row_lo, row_hi;
+};
+static_assert(sizeof(JoinDesc) == 48, "JoinDesc");
+
 __global__ void k_qaux(const DescRec *q, const int64_t *q_off, int nq, int64_t nd, double rough, QAux *aux,
-                       uint64_t *skey, uint32_t *sidx) {
+                       uint64_t *skey, uint32_t *sidx, JoinDesc *jd, double band, uint32_t frame_lo,
+                       uint32_t *votes, int64_t F) {
   const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nd) return;
   const DescRec r = q[d];
@@ -97,6 +109,20 @@ __global__ void k_qaux(const DescRec *q, const int64_t *q_off, int nq, int64_t n
   while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (q_off[mid] <= d) lo = mid; else hi = mid - 1; }
   a.qi = (uint32_t)lo;
   aux[d] = a;
+  if (jd) {
+    JoinDesc j;
+    j.s0a = j.s0b = (float)r.s[0]; j.s1a = j.s1b = (float)r.s[1]; j.s2a = j.s2b = (float)r.s[2];
+    j.nta = j.ntb = -(float)a.thr2;
+    // half-width of the decision band of the join's pre-filter: FP32 rounding (relative to thr^2, see
+    // k_vote_join) + the 13-bit cell-relative entries (each side off by <= 2^-14, ||delta|| <= 1.06e-4, so
+    // | ||q-e^||^2 - ||q-e||^2 | <= 2 thr ||delta|| + ||delta||^2 at the boundary; x1.5)
+    j.wband = __float_as_uint(__double2float_ru(a.thr2 * band + 3.3e-4 * sqrt(a.thr2) + 2e-8));
+    // (src.frame_id_ - db.frame_id_) > 0 on unsigned == "!=" (STDesc.cpp:373); relative to this shard
+    j.qframe = r.frame - frame_lo;
+    const unsigned long long rowp = (unsigned long long)(votes + (size_t)lo * (size_t)F);
+    j.row_lo = (uint32_t)rowp; j.row_hi = (uint32_t)(rowp >> 32);
+    jd[d] = j;
+  }
   if (skey) {  // label code major, then the descriptor's own cell: neighbours in this order share buckets
     const uint64_t k = probe_cell_key(r, 13);
     skey[d] = ((k & 0xFFFull) << 48) | (k >> 12);
@@ -339,6 +365,13 @@ __device__ __noinline__ uint32_t join_exact(const JoinParams &P, const double *q
   return hits;
 }
 
+// votes[row + frame] += 1 where sd < neg_wb: compare, address and RED in one asm block
+__device__ __forceinline__ void red_inc_lt(uint32_t *row, uint32_t frame, float sd, float neg_wb) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .u64 a;\n setp.lt.f32 p, %2, %3;\n mad.wide.u32 a, %1, 4, %0;\n @p red.global.add.u32 [a], 1;\n}" ::"l"(row),
+      "r"(frame), "f"(sd), "f"(neg_wb)
+      : "memory");
+}
 // votes[...] += 1 where `hit`: one predicated RED instead of a branch around it
 __device__ __forceinline__ void red_inc_if(uint32_t *addr, bool hit) {
   asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0;\n @p red.global.add.u32 [%0], 1;\n}" ::"l"(addr), "r"((uint32_t)hit)
@@ -444,6 +477,361 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
     if (lane == 0 && cM64) atomicAdd(P.counters + 4, cM64);
   }
 }
+
+// ============================ vote: segment joins on 8-byte entries ======================
+// Experimental second generation of the join (options join_impl 0 / 2; NOT the default: on the bench
+// workload they need 24 GB of DRAM traffic instead of 41 GB but 9.7e9 instead of 7.0e9 warp instructions
+// -- decoding the entries and lower lane utilisation of 256-entry tiles -- and the kernel is bound by
+// instruction issue).  Same work split as k_vote_join -- one warp per segment of kJoinSeg
+// consecutive sorted probes, a bucket streamed once per run of equal (group, bucket) keys -- but:
+//  * the bucket entries are 8 bytes instead of 16: the three sides RELATIVE TO THE BUCKET'S CELL in
+//    13-bit fixed point + the 25-bit local frame index (database.cu k_gather_index).  The kernel is bound
+//    by the DRAM traffic of the entries it streams (one pass over the probed buckets per query group), so
+//    halving the entry halves its dominant traffic.  The coarser entries only widen the band inside which
+//    the exact FP64 expression is evaluated (JoinDesc.wband, proven bound in k_qaux): decisions are still
+//    the reference's, bit for bit;
+//  * the per-descriptor operands (float sides and -thr^2 duplicated into f32x2 pairs, band half-width,
+//    relative query frame, vote-row pointer) are prepared ONCE per batch by k_qaux (JoinDesc, 48 B); a
+//    segment gathers its 32 records with three 16-byte loads per lane instead of converting 32 descriptors;
+//  * the frame-id test is only compiled into the path taken by probes whose query frame lies inside this
+//    shard's range (never the case for the node's queries, which carry current_frame_id_).
+// Two tile pipelines over the same inner loop:
+//   k_vote_join8  per-lane 16-byte evict-first loads straight into registers (default)
+//   k_vote_run    ONE lane issues 1-D bulk async copies (cp.async.bulk ... mbarrier::complete_tx::bytes,
+//                 L2 evict-first hint) into a ring of kRunSlots shared-memory slots per warp, kept
+//                 kRunSlots - 1 tiles ahead across run boundaries (all bucket headers of the segment are
+//                 read up front); measured slower on this workload -- most buckets are a few hundred
+//                 bytes and the per-copy cost of the bulk engine is not amortised -- kept as option
+//                 join_impl = 2 (DESIGN.md section 4 has the numbers).
+constexpr int kJ8U = 8;                  // entries per lane
+constexpr int kJ8Tile = 32 * kJ8U;       // entries per tile (2 KB)
+constexpr int kRunWarps = kVoteThreads / 32;
+constexpr int kRunSlots = 3;             // tiles in flight per warp (k_vote_run)
+
+// statistics for the roofline record (option stats_unique): distinct probed buckets of the batch and the
+// entries they hold -- what a vote kernel has to read at least once whatever its formulation
+__global__ void k_unique_stats(const uint32_t *pkey, unsigned long long npairs, const Bucket *table, uint32_t slot_mask,
+                               uint32_t *bitmap, unsigned long long *out /* buckets, entries */) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npairs) return;
+  const uint32_t k = pkey[i];
+  if (i && pkey[i - 1] == k) return;  // not a run head
+  const uint32_t slot = k & slot_mask;
+  const uint32_t bit = 1u << (slot & 31u);
+  if (atomicOr(&bitmap[slot >> 5], bit) & bit) return;  // the same bucket in another query group
+  atomicAdd(out, 1ull);
+  atomicAdd(out + 1, (unsigned long long)table[slot].cnt);
+}
+struct RunParams {
+  const uint32_t *pkey, *pval;
+  unsigned long long npairs;
+  const JoinDesc *jd;
+  const DescRec *q; const QAux *aux;
+  const Bucket *table;
+  const double *s0, *s1, *s2; const uint32_t *fr;
+  const uint64_t *pack8;
+  int64_t F;
+  unsigned long long *ticket, *counters;
+  uint32_t slot_mask;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra WAIT_%=;\n}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk async copy global -> shared, completion on an mbarrier, L2 evict-first (the tile is used once)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+// exact (reference) evaluation of the entries a lane found inside the decision band.  Takes the few
+// pointers it needs by value: a reference to the kernel's parameter struct would force a stack copy of it.
+// Entry u of a lane sits at  first + 64 * (u / 2) + (u & 1)  (see tile_to_regs).
+template <bool kDoVote>
+__device__ __noinline__ uint32_t run_exact(const DescRec *q, const QAux *aux, const double *s0, const double *s1,
+                                           const double *s2, const uint32_t *frp, uint32_t d, uint32_t *row, size_t first,
+                                           uint32_t amb) {
+  const DescRec r = q[d];
+  const double thr2 = aux[d].thr2;
+  uint32_t hits = 0;
+  while (amb) {
+    const int u = __ffs(amb) - 1;
+    amb &= amb - 1;
+    const size_t idx = first + 64 * (u >> 1) + (u & 1);
+    const double d2 = sqn3(__dsub_rn(r.s[0], s0[idx]), __dsub_rn(r.s[1], s1[idx]), __dsub_rn(r.s[2], s2[idx]));
+    if (d2 < thr2) {
+      if (kDoVote) atomicAdd(row + frp[idx], 1u);
+      ++hits;
+    }
+  }
+  return hits;
+}
+
+// Two packed entries (one 16-byte word pair) -> cell-relative float sides and frame indices.
+__device__ __forceinline__ void decode8(unsigned long long w, float &x, float &y, float &z, uint32_t &fr) {
+  constexpr float kScale = 1.0f / (float)(1 << kPack8Bits), kBias = 0.5f / (float)(1 << kPack8Bits) - 0.5f;
+  constexpr uint32_t kMask = (1u << kPack8Bits) - 1u;
+  x = fmaf((float)((uint32_t)w & kMask), kScale, kBias);
+  y = fmaf((float)((uint32_t)(w >> kPack8Bits) & kMask), kScale, kBias);
+  z = fmaf((float)((uint32_t)(w >> (2 * kPack8Bits)) & kMask), kScale, kBias);
+  fr = (uint32_t)(w >> kPack8FrameShift);
+}
+// The kJ8U entries of a lane: load k (0..3) of the tile covers entries 2 * (32 k + lane) and + 1, i.e. the
+// warp reads 512 contiguous bytes per load.  Entries past the end of the bucket are put at infinity:
+// neither a match nor ambiguous.  "+ (-0)" (the identity) makes each pair the result of a packed
+// instruction, i.e. pins it in an aligned register pair for the whole run.
+__device__ __forceinline__ void tile_to_regs(const ulonglong2 (&v)[kJ8U / 2], int lane, uint32_t n, f32x2 (&X)[kJ8U / 2],
+                                             f32x2 (&Y)[kJ8U / 2], f32x2 (&Z)[kJ8U / 2], uint32_t (&fr)[kJ8U]) {
+  const f32x2 negzero2 = pack2(-0.f, -0.f);
+#pragma unroll
+  for (int k = 0; k < kJ8U / 2; ++k) {
+    float xa, ya, za, xb, yb, zb;
+    decode8(v[k].x, xa, ya, za, fr[2 * k]);
+    decode8(v[k].y, xb, yb, zb, fr[2 * k + 1]);
+    const uint32_t e = 2 * (32 * k + lane);
+    if (e >= n) xa = __int_as_float(0x7f800000);
+    if (e + 1 >= n) xb = __int_as_float(0x7f800000);
+    X[k] = add2(pack2(xa, xb), negzero2);
+    Y[k] = add2(pack2(ya, yb), negzero2);
+    Z[k] = add2(pack2(za, zb), negzero2);
+  }
+}
+
+// one probe against the kJ8U entries a lane holds.  Q*: the probe's sides relative to the bucket's cell.
+// kCheckFrame: the query's own keyframe is in this shard.
+template <bool kDoVote, bool kCheckFrame>
+__device__ __forceinline__ uint32_t probe8(const RunParams &P, const f32x2 (&X)[kJ8U / 2], const f32x2 (&Y)[kJ8U / 2],
+                                           const f32x2 (&Z)[kJ8U / 2], const uint32_t (&fr)[kJ8U], f32x2 Q0, f32x2 Q1, f32x2 Q2,
+                                           f32x2 NT, const uint4 g, uint32_t d, size_t first) {
+  const float wb = __uint_as_float(g.x);
+  uint32_t *row = reinterpret_cast<uint32_t *>(((unsigned long long)g.w << 32) | g.z);
+  float sd[kJ8U];  // ||q - e||^2 - thr^2
+#pragma unroll
+  for (int j = 0; j < kJ8U / 2; ++j) {
+    const f32x2 dx = sub2(Q0, X[j]), dy = sub2(Q1, Y[j]), dz = sub2(Q2, Z[j]);
+    unpack2(fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, NT))), sd[2 * j], sd[2 * j + 1]);
+  }
+  uint32_t cM = 0;
+  float nearest = __int_as_float(0x7f800000);
+#pragma unroll
+  for (int u = 0; u < kJ8U; ++u) {
+    if (kDoVote && !kCheckFrame) {
+      red_inc_lt(row, fr[u], sd[u], -wb);  // certainly a match
+    } else {
+      bool hit = sd[u] < -wb;
+      if (kCheckFrame) hit = hit && (fr[u] != g.y);
+      if (kDoVote) red_inc_if(row + fr[u], hit);
+      else cM += hit;
+    }
+    nearest = fminf(nearest, fabsf(sd[u]));
+  }
+  if (nearest <= wb) {  // rare: some entry is inside the decision band
+    uint32_t amb = 0;
+#pragma unroll
+    for (int u = 0; u < kJ8U; ++u)
+      if ((!kCheckFrame || fr[u] != g.y) && fabsf(sd[u]) <= wb) amb |= 1u << u;
+    if (amb) cM += run_exact<kDoVote>(P.q, P.aux, P.s0, P.s1, P.s2, P.fr, d, row, first, amb);
+  }
+  return cM;
+}
+
+// all probes [p0, p0 + run) of the segment (operands in shared memory) against the tile in registers
+template <bool kDoVote>
+__device__ __forceinline__ uint32_t run_vs_tile(const RunParams &P, const uint4 (*sq)[3], const uint32_t *sd_, int p0, int run,
+                                                uint64_t bkey, const f32x2 (&X)[kJ8U / 2], const f32x2 (&Y)[kJ8U / 2],
+                                                const f32x2 (&Z)[kJ8U / 2], const uint32_t (&fr)[kJ8U], size_t first) {
+  // the bucket's cell (key = x:16 | y:16 | z:16 | code:12)
+  const float cx = (float)(uint32_t)(bkey >> 44), cy = (float)(uint32_t)((bkey >> 28) & 0xFFFF), cz = (float)(uint32_t)((bkey >> 12) & 0xFFFF);
+  const f32x2 C0 = pack2(cx, cx), C1 = pack2(cy, cy), C2 = pack2(cz, cz);
+  uint32_t cM = 0;
+  for (int p = p0; p < p0 + run; ++p) {
+    const uint4 qa = sq[p][0], qb = sq[p][1], g = sq[p][2];
+    const f32x2 Q0 = sub2(((unsigned long long)qa.y << 32) | qa.x, C0), Q1 = sub2(((unsigned long long)qa.w << 32) | qa.z, C1);
+    const f32x2 Q2 = sub2(((unsigned long long)qb.y << 32) | qb.x, C2), NT = ((unsigned long long)qb.w << 32) | qb.z;
+    if (g.y < (uint32_t)P.F) cM += probe8<kDoVote, true>(P, X, Y, Z, fr, Q0, Q1, Q2, NT, g, sd_[p], first);
+    else cM += probe8<kDoVote, false>(P, X, Y, Z, fr, Q0, Q1, Q2, NT, g, sd_[p], first);
+  }
+  return cM;
+}
+
+// ---- default: per-lane evict-first loads -------------------------------------------------------------
+template <bool kDoVote>
+__global__ void __launch_bounds__(kVoteThreads, 3) k_vote_join8(RunParams P) {
+  __shared__ __align__(16) uint4 sh_q[kRunWarps][32][3];  // JoinDesc of the segment's probes
+  __shared__ uint32_t sh_d[kRunWarps][32];                // their descriptor indices (exact path)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned long long nseg = (P.npairs + kJoinSeg - 1) / kJoinSeg;
+  uint32_t cM = 0;
+  while (true) {
+    unsigned long long seg = 0;
+    if (lane == 0) seg = atomicAdd(P.ticket, 1ull);
+    seg = __shfl_sync(0xffffffffu, seg, 0);
+    if (seg >= nseg) break;
+    const unsigned long long pbase = seg * kJoinSeg;
+    const int np = (int)min((unsigned long long)kJoinSeg, P.npairs - pbase);
+    // ---- the segment's probes: bucket header and JoinDesc of each, all loads independent
+    uint32_t key = 0xFFFFFFFFu, b_off = 0, b_cnt = 0, k_lo = 0, k_hi = 0;
+    __syncwarp();
+    if (lane < np) {
+      key = P.pkey[pbase + lane];
+      const uint32_t d = P.pval[pbase + lane];
+      const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.table[key & P.slot_mask]));
+      k_lo = raw.x; k_hi = raw.y; b_off = raw.z; b_cnt = raw.w;
+      const uint4 *src = reinterpret_cast<const uint4 *>(P.jd + d);
+      const uint4 j0 = __ldg(src), j1 = __ldg(src + 1), j2 = __ldg(src + 2);
+      sh_q[wid][lane][0] = j0; sh_q[wid][lane][1] = j1; sh_q[wid][lane][2] = j2;
+      sh_d[wid][lane] = d;
+    }
+    __syncwarp();
+    int i = 0;
+    while (i < np) {
+      const uint32_t cur = __shfl_sync(0xffffffffu, key, i);
+      const int run = __popc(__ballot_sync(0xffffffffu, key == cur));  // sorted: equal keys are contiguous from i
+      const uint32_t off = __shfl_sync(0xffffffffu, b_off, i), n = __shfl_sync(0xffffffffu, b_cnt, i);
+      const uint64_t bkey = ((uint64_t)__shfl_sync(0xffffffffu, k_hi, i) << 32) | __shfl_sync(0xffffffffu, k_lo, i);
+      const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(P.pack8 + off);  // 8-byte aligned; see below
+      for (uint32_t e0 = 0; e0 < n; e0 += kJ8Tile) {
+        // the bucket starts at an arbitrary 8-byte boundary: two 8-byte streaming loads per pair (evict-first,
+        // the tile is used once and must not push the vote rows out of L2), all issued before the first use
+        ulonglong2 v[kJ8U / 2];
+#pragma unroll
+        for (int k = 0; k < kJ8U / 2; ++k) {
+          const uint32_t e = e0 + 2 * (32 * k + lane);
+          const uint64_t *p = P.pack8 + (size_t)off + (e < n ? e : n - 1);
+          v[k].x = __ldcs(reinterpret_cast<const unsigned long long *>(p));
+          v[k].y = __ldcs(reinterpret_cast<const unsigned long long *>(p + (e + 1 < n ? 1 : 0)));
+        }
+        (void)src;
+        f32x2 X[kJ8U / 2], Y[kJ8U / 2], Z[kJ8U / 2];
+        uint32_t fr[kJ8U];
+        tile_to_regs(v, lane, n - e0, X, Y, Z, fr);
+        cM += run_vs_tile<kDoVote>(P, sh_q[wid], sh_d[wid], i, run, bkey, X, Y, Z, fr, (size_t)off + e0 + 2 * lane);
+      }
+      i += run;
+    }
+  }
+  if (!kDoVote) {
+    unsigned long long cM64 = cM;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cM64 += __shfl_xor_sync(0xffffffffu, cM64, o);
+    if (lane == 0 && cM64) atomicAdd(P.counters + 4, cM64);
+  }
+}
+
+// ---- option join_impl = 2: bulk-async staged tiles --------------------------------------------------------
+// A bucket starts at an arbitrary 8-byte boundary but a bulk copy needs 16-byte alignment: the copy starts at
+// the preceding 16-byte boundary and `skew` (0 or 1 entries) is carried to the register load.
+template <bool kDoVote>
+__global__ void __launch_bounds__(kVoteThreads, 3) k_vote_run(RunParams P) {
+  extern __shared__ __align__(128) unsigned char sh_raw[];
+  // [warp][slot][kJ8Tile + 2] packed entries (bulk async copy targets), then [warp][32][3] JoinDesc words
+  constexpr int kSlotWords = kJ8Tile + 2;
+  uint64_t (*sh_tile)[kRunSlots][kSlotWords] = reinterpret_cast<uint64_t (*)[kRunSlots][kSlotWords]>(sh_raw);
+  uint4 (*sh_q)[32][3] = reinterpret_cast<uint4 (*)[32][3]>(sh_raw + sizeof(uint64_t) * kRunWarps * kRunSlots * kSlotWords);
+  __shared__ uint32_t sh_d[kRunWarps][32];
+  __shared__ __align__(8) uint64_t sh_bar[kRunWarps][kRunSlots];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned long long nseg = (P.npairs + kJoinSeg - 1) / kJoinSeg;
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  if (lane < kRunSlots) mbar_init(&sh_bar[wid][lane], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  uint32_t cM = 0;
+  uint32_t used = 0;  // copies issued so far by this warp: slot = used % kRunSlots
+  uint32_t done = 0;  // tiles consumed so far: parity = (done / kRunSlots) & 1
+
+  while (true) {
+    unsigned long long seg = 0;
+    if (lane == 0) seg = atomicAdd(P.ticket, 1ull);
+    seg = __shfl_sync(0xffffffffu, seg, 0);
+    if (seg >= nseg) break;
+    const unsigned long long pbase = seg * kJoinSeg;
+    const int np = (int)min((unsigned long long)kJoinSeg, P.npairs - pbase);
+    uint32_t key = 0xFFFFFFFFu, b_off = 0, b_cnt = 0, k_lo = 0, k_hi = 0;
+    if (lane < np) {
+      key = P.pkey[pbase + lane];
+      const uint32_t d = P.pval[pbase + lane];
+      const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.table[key & P.slot_mask]));
+      k_lo = raw.x; k_hi = raw.y; b_off = raw.z; b_cnt = raw.w;
+      const uint4 *src = reinterpret_cast<const uint4 *>(P.jd + d);
+      const uint4 j0 = __ldg(src), j1 = __ldg(src + 1), j2 = __ldg(src + 2);
+      sh_q[wid][lane][0] = j0; sh_q[wid][lane][1] = j1; sh_q[wid][lane][2] = j2;
+      sh_d[wid][lane] = d;
+    }
+    // run heads (sorted: equal keys are contiguous) and, per lane, the length of the run starting there
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane < np && (lane == 0 || key != prev));
+    const unsigned above = heads & ~((2u << lane) - 1u);  // heads after this lane
+    const int run_l = (above ? __ffs(above) - 1 : np) - lane;
+    __syncwarp();
+
+    // cursors over the flat list of (run, tile) of this segment: ci = next copy to issue, cc = tile to test
+    int ci_i = 0, cc_i = 0;
+    uint32_t ci_k = 0, cc_k = 0;
+    auto issue = [&]() {  // copy of tile ci_k of the run starting at probe ci_i; advances the cursor
+      const uint32_t off = __shfl_sync(0xffffffffu, b_off, ci_i), cnt = __shfl_sync(0xffffffffu, b_cnt, ci_i);
+      const int run = __shfl_sync(0xffffffffu, run_l, ci_i);
+      const uint32_t e0 = ci_k * kJ8Tile, n = min((uint32_t)kJ8Tile, cnt - e0);
+      if (lane == 0) {
+        uint64_t *bar = &sh_bar[wid][used % kRunSlots];
+        const uint32_t skew = (off + e0) & 1u;
+        const uint32_t bytes = ((n + skew + 1u) & ~1u) * 8u;  // whole 16-byte words (the index is padded by 4 entries)
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(&sh_tile[wid][used % kRunSlots][0], P.pack8 + (size_t)off + e0 - skew, bytes, bar, policy);
+      }
+      ++used;
+      if (e0 + kJ8Tile < cnt) ++ci_k; else { ci_i += run; ci_k = 0; }
+    };
+#pragma unroll 1
+    for (int s = 0; s < kRunSlots && ci_i < np; ++s) issue();
+
+    while (cc_i < np) {
+      const uint32_t off = __shfl_sync(0xffffffffu, b_off, cc_i), cnt = __shfl_sync(0xffffffffu, b_cnt, cc_i);
+      const int run = __shfl_sync(0xffffffffu, run_l, cc_i);
+      const uint64_t bkey = ((uint64_t)__shfl_sync(0xffffffffu, k_hi, cc_i) << 32) | __shfl_sync(0xffffffffu, k_lo, cc_i);
+      const uint32_t e0 = cc_k * kJ8Tile, n = min((uint32_t)kJ8Tile, cnt - e0);
+      const uint32_t slot = done % kRunSlots, skew = (off + e0) & 1u;
+      mbar_wait(&sh_bar[wid][slot], (done / kRunSlots) & 1u);
+      ++done;
+      // ---- the tile's entries into registers; the slot is then free for the copy kRunSlots tiles ahead
+      ulonglong2 v[kJ8U / 2];
+#pragma unroll
+      for (int k = 0; k < kJ8U / 2; ++k) {
+        const uint32_t e = 2 * (32 * k + lane);
+        const uint64_t *p = &sh_tile[wid][slot][skew + (e < n ? e : n - 1)];
+        v[k].x = p[0]; v[k].y = p[e + 1 < n ? 1 : 0];
+      }
+      f32x2 X[kJ8U / 2], Y[kJ8U / 2], Z[kJ8U / 2];
+      uint32_t fr[kJ8U];
+      tile_to_regs(v, lane, n, X, Y, Z, fr);
+      __syncwarp();
+      if (ci_i < np) issue();
+      cM += run_vs_tile<kDoVote>(P, sh_q[wid], sh_d[wid], cc_i, run, bkey, X, Y, Z, fr, (size_t)off + e0 + 2 * lane);
+      if (e0 + kJ8Tile < cnt) ++cc_k; else { cc_i += run; cc_k = 0; }
+    }
+    __syncwarp();  // sh_q / sh_d are rewritten by the next segment
+  }
+  if (!kDoVote) {
+    unsigned long long cM64 = cM;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cM64 += __shfl_xor_sync(0xffffffffu, cM64, o);
+    if (lane == 0 && cM64) atomicAdd(P.counters + 4, cM64);
+  }
+}
+constexpr size_t kRunSmem = sizeof(uint64_t) * kRunWarps * kRunSlots * (kJ8Tile + 2) + sizeof(uint4) * kRunWarps * 32 * 3;
 
 // ============================ top-k ==============================================
 constexpr int kTopkThreads = 256;
@@ -596,16 +984,16 @@ void merge_topk_host(const int32_t *votes, const int32_t *frames, int nlists, in
   for (int i = 0; i < nlists * k; ++i) merge_rank(votes, frames, nlists * k, i, k, out_votes, out_frames);
 }
 
-// gathered: [nranks][nq][k] ; out: [nq][k]
-__global__ void k_merge(const int32_t *g_votes, const int32_t *g_frames, int nranks, int nq, int k,
-                        int32_t *out_votes, int32_t *out_frames) {
+// gathered: one allgather of every rank's {votes[nq][k], frames[nq][k]} block ; out: [nq][k]
+__global__ void k_merge(const int32_t *gathered, int nranks, int nq, int k, int32_t *out_votes, int32_t *out_frames) {
   extern __shared__ int32_t s_m[];
   int32_t *sv = s_m, *sf = s_m + nranks * k;
   const int q = blockIdx.x;
+  const size_t nslot = (size_t)nq * k;
   for (int i = threadIdx.x; i < nranks * k; i += blockDim.x) {
     const int rk = i / k, c = i - rk * k;
-    sv[i] = g_votes[((size_t)rk * nq + q) * k + c];
-    sf[i] = g_frames[((size_t)rk * nq + q) * k + c];
+    sv[i] = gathered[(size_t)rk * 2 * nslot + (size_t)q * k + c];
+    sf[i] = gathered[(size_t)rk * 2 * nslot + nslot + (size_t)q * k + c];
   }
   for (int i = threadIdx.x; i < k; i += blockDim.x) { out_votes[(size_t)q * k + i] = 0; out_frames[(size_t)q * k + i] = -1; }
   __syncthreads();
@@ -830,8 +1218,22 @@ constexpr int kIndexThreads = 1024;
 // One CTA per query: clears the query's table (it then sits in L2: 148 resident tables of ~0.6 MB) and
 // inserts every probe with one CAS.
 __global__ void __launch_bounds__(kIndexThreads) k_query_index(const DescRec *q, const QAux *aux, const int64_t *q_off,
-                                                               int q_base, unsigned long long *qt, uint32_t ts) {
+                                                               int q_base, unsigned long long *qt, uint32_t ts,
+                                                               const sgtd_candidate *cands, int k) {
   const int qi = q_base + blockIdx.x;  // tables are indexed by the query's position inside its group
+  // a query none of whose candidates is materialised on this rank (sharded database: the candidates of a
+  // query cluster in one or two keyframe-range shards) needs no table
+  {
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < k) {
+      const sgtd_candidate &c = cands[(size_t)qi * k + threadIdx.x];
+      if (c.match_off >= 0 && c.nmatch > 0) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) return;
+  }
   const int64_t q0 = q_off[qi], q1 = q_off[qi + 1];
   unsigned long long *tk = qt + (size_t)blockIdx.x * ts;
   const uint32_t mask = ts - 1;
@@ -1456,19 +1858,40 @@ __global__ void __launch_bounds__(kVerifyThreads, 5) k_verify(VerifyParams P) {
   }
 }
 
-// multi-shard: take each slot's record from the rank that owns the keyframe
-__global__ void k_pick_owner(const sgtd_candidate *gathered, int nranks, int rank, int n, int64_t frames_per_rank,
-                             sgtd_candidate *cands) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+// multi-shard: what verification produced for a slot (score, inlier count, hypothesis, pose) is only known to
+// the rank that owns the candidate's keyframe.  Every slot has exactly one owner, so the owner writes the
+// payload (27 32-bit words), the others zeros, and ONE sum all-reduce over NVLink/NVSwitch hands every
+// rank every payload (integer sums with zeros: bit patterns of the doubles are preserved).
+constexpr int kPayWords = 3 + 24;
+__global__ void k_pack_payload(const sgtd_candidate *cands, int n, uint32_t *pay) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int f = cands[i].frame;
-  if (f < 0) return;
-  int owner = (int)(f / frames_per_rank);
-  if (owner >= nranks) owner = nranks - 1;
-  if (owner == rank) return;  // own record (with this rank's match/inlier offsets) stays
-  sgtd_candidate c = gathered[(size_t)owner * n + i];
-  c.match_off = -1; c.inlier_off = -1;  // lists live on the owner
-  cands[i] = c;
+  uint32_t *o = pay + (size_t)i * kPayWords;
+  const sgtd_candidate &c = cands[i];
+  if (c.match_off < 0 || c.frame < 0) {
+#pragma unroll
+    for (int w = 0; w < kPayWords; ++w) o[w] = 0u;
+    return;
+  }
+  o[0] = (uint32_t)c.score; o[1] = (uint32_t)c.ninlier; o[2] = (uint32_t)c.best_hyp;
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(j < 9 ? c.R[j] : c.t[j - 9]);
+    o[3 + 2 * j] = (uint32_t)b; o[4 + 2 * j] = (uint32_t)(b >> 32);
+  }
+}
+__global__ void k_unpack_payload(const uint32_t *pay, int n, sgtd_candidate *cands) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sgtd_candidate &c = cands[i];
+  if (c.frame < 0 || c.match_off >= 0) return;  // empty slot, or this rank's own record (keeps its list offsets)
+  const uint32_t *o = pay + (size_t)i * kPayWords;
+  c.score = (int32_t)o[0]; c.ninlier = (int32_t)o[1]; c.best_hyp = (int32_t)o[2];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    const double v = __longlong_as_double((long long)(((unsigned long long)o[4 + 2 * j] << 32) | o[3 + 2 * j]));
+    if (j < 9) c.R[j] = v; else c.t[j - 9] = v;
+  }
 }
 
 // SearchLoop tail (STDesc.cpp:103-146): first strict maximum of the scores.
@@ -1516,21 +1939,19 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   size_t cubb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, cubb, (int64_t *)nullptr, (int64_t *)nullptr, (int)nslot + 1, st);
   size_t o = 0;
-  size_t o_lv = o; o += al(nslot * 4);
-  size_t o_lf = o; o += al(nslot * 4);
-  size_t o_gv = o; o += al(nslot * 4 * h->nranks);
-  size_t o_gf = o; o += al(nslot * 4 * h->nranks);
+  size_t o_lv = o, o_lf = o + nslot * 4;      // local top-k: votes then frames, contiguous (one allgather)
+  o += al(nslot * 8);
+  size_t o_gv = o; o += al(nslot * 8 * h->nranks);
   size_t o_mv = o; o += al(nslot * 4);
   size_t o_mf = o; o += al(nslot * 4);
   size_t o_cnt = o; o += al((nslot + 1) * 8);
   size_t o_off = o; o += al((nslot + 1) * 8);
   size_t o_cub = o; o += al(cubb);
-  size_t o_gc = o; o += (h->nranks > 1) ? al(nslot * sizeof(sgtd_candidate) * h->nranks) : 0;
+  size_t o_gc = o; o += (h->nranks > 1) ? al(nslot * kPayWords * 4) : 0;
   size_t o_aux = o; o += al((size_t)std::max<int64_t>(qb->n, 1) * sizeof(QAux));
   // vote formulation: bucket-major join (default) or per-probe streaming (SGTD_VOTE_MODE=stream)
-  const char *vmode = getenv("SGTD_VOTE_MODE");
   bool m_by_topk = false;  // the join leaves the match count (stats) to k_topk
-  const bool join_mode = !(vmode && strcmp(vmode, "stream") == 0) && qb->n > 0 && h->rec.n > 0;
+  const bool join_mode = !h->opt.vote_stream && qb->n > 0 && h->rec.n > 0;
   bool join_timed = false;
   const bool sort_q = !join_mode && qb->n > 0;  // streaming mode walks descriptors in cell-key order (L2 reuse)
   size_t cubj = 0;
@@ -1554,23 +1975,29 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   uint32_t qt_ts = 64;
   while ((int64_t)qt_ts < 32 * max_dq) qt_ts <<= 1;
   // all queries of the batch in one group: splitting the batch so that the tables stay L2-resident was
-  // measured slower (too little parallelism per launch); SGTD_COLLECT_GROUP overrides for experiments
-  const int qt_group = getenv("SGTD_COLLECT_GROUP") ? std::max(1, atoi(getenv("SGTD_COLLECT_GROUP"))) : std::max(nq, 1);
+  // measured slower (too little parallelism per launch); option collect_group overrides for experiments
+  const int qt_group = h->opt.collect_group > 0 ? h->opt.collect_group : std::max(nq, 1);
   size_t o_qtk = o; o += al((size_t)qt_group * qt_ts * 8);
   size_t o_jc = o; o += al(64);
+  const bool run_join = join_mode && h->opt.join_impl != 1;
+  size_t o_jd = o; o += run_join ? al((size_t)std::max<int64_t>(qb->n, 1) * sizeof(JoinDesc)) : 0;
   size_t o_pose = o; o += al((size_t)std::max(nq * k, 1) * kMaxHyp * 12 * sizeof(double));
   size_t o_jcub = o; o += al(cubj);
   SGTD_CUDA(h, h->scratch.reserve(o, st, false));
   unsigned char *S = h->scratch.p;
-  int32_t *lv = (int32_t *)(S + o_lv), *lf = (int32_t *)(S + o_lf), *gv = (int32_t *)(S + o_gv), *gf = (int32_t *)(S + o_gf);
+  int32_t *lv = (int32_t *)(S + o_lv), *lf = (int32_t *)(S + o_lf), *gv = (int32_t *)(S + o_gv);
   int32_t *mv = (int32_t *)(S + o_mv), *mf = (int32_t *)(S + o_mf);
   int64_t *cnt = (int64_t *)(S + o_cnt), *off = (int64_t *)(S + o_off);
 
   QAux *aux = (QAux *)(S + o_aux);
+  // half-width of the FP32 decision band of the join's pre-filter, relative to thr^2 (see k_vote_join)
+  const double join_band = 2.5e-6 * (1.0 + 1.0 / h->c.rough);
   SGTD_CUDA(h, cudaEventRecord(ev[0], st));
   if (qb->n > 0) {
     k_qaux<<<(unsigned)((qb->n + 255) / 256), 256, 0, st>>>(qb->rec.p, qb->d_off.p, nq, qb->n, h->c.rough, aux,
-                                                             sort_q ? (uint64_t *)(S + o_sk0) : nullptr, (uint32_t *)(S + o_si0));
+                                                             sort_q ? (uint64_t *)(S + o_sk0) : nullptr, (uint32_t *)(S + o_si0),
+                                                             run_join ? (JoinDesc *)(S + o_jd) : nullptr, join_band,
+                                                             (uint32_t)h->frame_lo(), r->votes.p, Fa);
     SGTD_LAUNCHED(h);
     if (sort_q) {
       SGTD_CUDA(h, cub::DeviceRadixSort::SortPairs(S + o_cubs, cubs, (uint64_t *)(S + o_sk0), (uint64_t *)(S + o_sk1),
@@ -1592,13 +2019,13 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
     const int64_t warps_needed = qb->n;
     int grid = (int)std::min<int64_t>((warps_needed * 32 + kVoteThreads - 1) / kVoteThreads, (int64_t)h->sm_count * 8);
     if (!join_mode) {
-      if (getenv("SGTD_DEBUG_NOVOTE")) k_vote<false><<<grid, kVoteThreads, 0, st>>>(V);
+      if (h->opt.debug_novote) k_vote<false><<<grid, kVoteThreads, 0, st>>>(V);
       else k_vote<true><<<grid, kVoteThreads, 0, st>>>(V);
       SGTD_LAUNCHED(h);
       SGTD_CUDA(h, cudaGetLastError());
     } else {
       unsigned long long *d_cursor = (unsigned long long *)(S + o_jc);
-      SGTD_CUDA(h, cudaMemsetAsync(d_cursor, 0, 16, st));
+      SGTD_CUDA(h, cudaMemsetAsync(d_cursor, 0, 32, st));
       EmitParams2 E2{};
       E2.q = qb->rec.p; E2.aux = aux; E2.nd = qb->n; E2.table = h->table.p; E2.mask = h->table_mask;
       E2.pkey = (uint32_t *)(S + o_jk0); E2.pval = (uint32_t *)(S + o_jv0);
@@ -1610,7 +2037,7 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
       // loads; measured optimum on B200 (126 MB L2): ~50 MB of rows per group.  More groups = fewer
       // probes per bucket run, so no more than needed.
       int ngroups = (int)std::min<int64_t>(32, std::max<int64_t>(1, ((int64_t)nq * Fa * 4 + (56ll << 20) - 1) / (56ll << 20)));
-      if (getenv("SGTD_JOIN_GROUPS")) ngroups = std::max(1, atoi(getenv("SGTD_JOIN_GROUPS")));
+      if (h->opt.join_groups > 0) ngroups = h->opt.join_groups;
       E2.group_shift = (uint32_t)sbits; E2.group_div = (uint32_t)std::max(1, (nq + ngroups - 1) / ngroups);
       int gbits = 0;
       while ((1 << gbits) < ngroups) ++gbits;
@@ -1629,15 +2056,50 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
         J.pkey = (uint32_t *)(S + o_jk1); J.pval = (uint32_t *)(S + o_jv1); J.npairs = npairs;
         J.q = qb->rec.p; J.aux = aux; J.table = h->table.p;
         J.s0 = h->v_s0.p; J.s1 = h->v_s1.p; J.s2 = h->v_s2.p; J.fr = h->v_frame.p;
-        J.pack = h->v_pack.p; J.band = 2.5e-6 * (1.0 + 1.0 / h->c.rough);
+        J.pack = h->v_pack.p; J.band = join_band;
         J.frame_lo = (uint32_t)h->frame_lo(); J.F = Fa; J.votes = r->votes.p;
         J.seg_counter = d_cursor + 1; J.counters = r->counters.p; J.slot_mask = (uint32_t)((1ull << sbits) - 1);
-        SGTD_CUDA(h, cudaEventRecord(ev[8], st));
         const int jgrid = h->sm_count * 4;
-        if (getenv("SGTD_DEBUG_NOVOTE")) k_vote_join<false><<<jgrid, kVoteThreads, 0, st>>>(J);
-        else { k_vote_join<true><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
-        SGTD_LAUNCHED(h);
-        SGTD_CUDA(h, cudaGetLastError());
+        if (h->opt.stats_unique) {
+          const size_t words = ((size_t)h->table_mask + 32) / 32;
+          SGTD_CUDA(h, h->uniq_bitmap.reserve(words, st, false));
+          SGTD_CUDA(h, cudaMemsetAsync(h->uniq_bitmap.p, 0, words * 4, st));
+          k_unique_stats<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(J.pkey, npairs, h->table.p, J.slot_mask,
+                                                                            h->uniq_bitmap.p, r->counters.p + 5);
+          SGTD_LAUNCHED(h);
+        }
+        if (!run_join) {
+          SGTD_CUDA(h, cudaEventRecord(ev[8], st));
+          if (h->opt.debug_novote) k_vote_join<false><<<jgrid, kVoteThreads, 0, st>>>(J);
+          else { k_vote_join<true><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
+          SGTD_LAUNCHED(h);
+          SGTD_CUDA(h, cudaGetLastError());
+        } else {
+          RunParams R{};
+          R.pkey = J.pkey; R.pval = J.pval; R.npairs = npairs;
+          R.jd = (const JoinDesc *)(S + o_jd); R.q = qb->rec.p; R.aux = aux; R.table = h->table.p;
+          R.s0 = J.s0; R.s1 = J.s1; R.s2 = J.s2; R.fr = J.fr; R.pack8 = h->v_pack8.p; R.F = Fa;
+          R.ticket = d_cursor + 1; R.counters = r->counters.p; R.slot_mask = J.slot_mask;
+          SGTD_CUDA(h, cudaEventRecord(ev[8], st));
+          const int rgrid = h->sm_count * 3;
+          if (h->opt.join_impl == 2) {
+            if (h->opt.debug_novote) {
+              SGTD_CUDA(h, cudaFuncSetAttribute(k_vote_run<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRunSmem));
+              k_vote_run<false><<<rgrid, kVoteThreads, kRunSmem, st>>>(R);
+            } else {
+              SGTD_CUDA(h, cudaFuncSetAttribute(k_vote_run<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRunSmem));
+              k_vote_run<true><<<rgrid, kVoteThreads, kRunSmem, st>>>(R);
+              m_by_topk = true;
+            }
+          } else if (h->opt.debug_novote) {
+            k_vote_join8<false><<<rgrid, kVoteThreads, 0, st>>>(R);
+          } else {
+            k_vote_join8<true><<<rgrid, kVoteThreads, 0, st>>>(R);
+            m_by_topk = true;
+          }
+          SGTD_LAUNCHED(h);
+          SGTD_CUDA(h, cudaGetLastError());
+        }
         join_timed = true;
       }
     }
@@ -1654,9 +2116,8 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   const int32_t *tv = lv, *tf = lf;
   if (h->nranks > 1 && h->nccl && nq > 0) {
     ncclComm_t comm = (ncclComm_t)h->nccl;
-    if (nccl_api().AllGather(lv, gv, nslot, ncclInt32, comm, st) != ncclSuccess) SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(votes)");
-    if (nccl_api().AllGather(lf, gf, nslot, ncclInt32, comm, st) != ncclSuccess) SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(frames)");
-    k_merge<<<nq, 128, (size_t)h->nranks * k * 8, st>>>(gv, gf, h->nranks, nq, k, mv, mf);
+    if (nccl_api().AllGather(lv, gv, 2 * nslot, ncclInt32, comm, st) != ncclSuccess) SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(top-k)");
+    k_merge<<<nq, 128, (size_t)h->nranks * k * 8, st>>>(gv, h->nranks, nq, k, mv, mf);
     SGTD_LAUNCHED(h);
     SGTD_CUDA(h, cudaGetLastError());
     tv = mv; tf = mf;
@@ -1681,11 +2142,10 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   SGTD_CUDA(h, r->m_cell.reserve(tm, st, false)); SGTD_CUDA(h, r->inl.reserve(tm, st, false));
   r->m_q.n = r->m_g.n = r->m_cell.n = r->inl.n = (size_t)total;
   if (total > 0) {
-    // The inverted form pays a fixed ~1.6 ms per 1,024 queries to build the per-query tables and then
-    // ~1/4 of the per-candidate cost of k_collect; with the database split over 8 shards a rank owns too
-    // few candidates per query to amortise the fixed part, so it is used up to 4 shards.
-    const char *cmode = getenv("SGTD_COLLECT_MODE");
-    const bool inverted = cmode ? strcmp(cmode, "desc") != 0 : h->nranks <= 4;
+    // The inverted form builds a per-query probe table (~1.6 ms per 1,024 queries when every query needs
+    // one) and then costs ~1/4 of k_collect per candidate.  On a sharded database only the queries with a
+    // candidate owned by this rank build their table (k_query_index), so it pays at every shard count.
+    const bool inverted = h->opt.collect_mode ? h->opt.collect_mode == 1 : true;
     if (inverted) {
       // per-query probe multimap, then one lookup per keyframe entry + shared-memory sort
       CollectInvParams I{};
@@ -1700,7 +2160,8 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
                                         2 * kSortCap * 4 + 2 * kInvMaxDesc));
       for (int qb0 = 0; qb0 < nq; qb0 += qt_group) {
         const int gq = std::min(qt_group, nq - qb0);
-        k_query_index<<<gq, kIndexThreads, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (unsigned long long *)(S + o_qtk), qt_ts);
+        k_query_index<<<gq, kIndexThreads, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (unsigned long long *)(S + o_qtk), qt_ts,
+                                                    r->cands.p, k);
         I.q_base = qb0;
         k_collect_inv<<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
         h->launches += 2;
@@ -1730,12 +2191,13 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   SGTD_CUDA(h, cudaEventRecord(ev[5], st));
   if (h->nranks > 1 && h->nccl && nq > 0) {
     ncclComm_t comm = (ncclComm_t)h->nccl;
-    sgtd_candidate *gc = (sgtd_candidate *)(S + o_gc);
-    if (nccl_api().AllGather(r->cands.p, gc, nslot * sizeof(sgtd_candidate), ncclUint8, comm, st) != ncclSuccess)
-      SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllGather(candidates)");
-    // keep this rank's own offsets for owned slots: k_pick_owner copies the owner's record, which for
-    // owned slots is this rank's own record.
-    k_pick_owner<<<(int)((nslot + 255) / 256), 256, 0, st>>>(gc, h->nranks, h->rank, (int)nslot, h->frames_per_rank, r->cands.p);
+    uint32_t *pay = (uint32_t *)(S + o_gc);
+    const int pb = (int)((nslot + 255) / 256);
+    k_pack_payload<<<pb, 256, 0, st>>>(r->cands.p, (int)nslot, pay);
+    SGTD_LAUNCHED(h);
+    if (nccl_api().AllReduce(pay, pay, nslot * kPayWords, ncclUint32, ncclSum, comm, st) != ncclSuccess)
+      SGTD_FAIL(h, SGTD_E_NCCL, "ncclAllReduce(candidate payloads)");
+    k_unpack_payload<<<pb, 256, 0, st>>>(pay, (int)nslot, r->cands.p);
     SGTD_LAUNCHED(h);
     SGTD_CUDA(h, cudaGetLastError());
   }

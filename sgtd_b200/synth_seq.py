@@ -156,3 +156,24 @@ def render_at(world, pose, seed, device="cpu", n_beams=64, n_az=1875, max_range=
     inten = torch.rand(int(keep.sum()), generator=g, dtype=dt).to(device)
     pts = torch.stack([dx[keep] * r, dy[keep] * r, dz[keep] * r, inten], dim=1).to(torch.float32)
     return pts, lab[keep]
+
+
+def make_dense_world(seed, n_cyl=2400, radius=62.0):
+    """configs[4]-shaped stress scene around the origin: thousands of poles / trunks inside `radius`,
+    a few facades; rendered with dense azimuth sampling it yields > 500 instance nodes per scan."""
+    rng = np.random.default_rng(seed)
+    r = np.sqrt(rng.uniform(4.0 ** 2, radius ** 2, n_cyl))
+    a = rng.uniform(-np.pi, np.pi, n_cyl)
+    kind = rng.random(n_cyl) < 0.5
+    ctr = 500.0   # mid-block of a 1,000 m grid: the whole footprint is terrain
+    cyl = np.column_stack([ctr + r * np.cos(a), ctr + r * np.sin(a), np.where(kind, rng.uniform(0.08, 0.16, n_cyl), rng.uniform(0.18, 0.35, n_cyl)),
+                           np.zeros(n_cyl), np.where(kind, rng.uniform(3.0, 6.5, n_cyl), rng.uniform(1.8, 3.2, n_cyl)),
+                           np.where(kind, POLE, TRUNK)])
+    rect = []
+    for _ in range(24):
+        ang, d, ln = rng.uniform(-np.pi, np.pi), rng.uniform(radius + 3, radius + 25), rng.uniform(10, 30)
+        c = np.array([ctr + d * np.cos(ang), ctr + d * np.sin(ang)])
+        t = np.array([-np.sin(ang), np.cos(ang)]) * ln / 2
+        rect.append((c[0] - t[0], c[1] - t[1], c[0] + t[0], c[1] + t[1], 0.0, rng.uniform(5, 12), BUILDING))
+    return dict(poses=np.array([[ctr, ctr, 0.3]]), G=2, block=1000.0, cyl=cyl, rect=np.array(rect, np.float64),
+                patches=np.zeros((0, 4)), road_half=3.5, walk=2.0, seed=seed)

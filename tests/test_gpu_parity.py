@@ -115,20 +115,23 @@ def test_search_parity(world, built):
     assert stats == tot
 
 
-def test_vote_formulations_agree(world, built, monkeypatch):
-    """The bucket-major join (default), the per-probe streaming kernel (SGTD_VOTE_MODE=stream) and
-    the join with several query groups give identical votes, counters and candidates; the inverted
-    match collection (default) and the per-descriptor one (SGTD_COLLECT_MODE=desc) identical lists."""
+def test_vote_formulations_agree(world, built):
+    """The join on 16-byte float entries (default, join_impl 1), the experimental joins on 8-byte
+    cell-relative entries (join_impl 0: per-lane loads; 2: bulk-async staged tiles), the per-probe streaming kernel (exact
+    FP64 on every entry) and the joins with several query groups give identical
+    votes, counters and candidates; the inverted match collection (default) and the per-descriptor one
+    identical lists.  The switches are handle options (sgtd_set_option); the search never reads the
+    environment."""
     mgr, o, *_ = built
     qx, ql, qo = world["queries"]
     qb = mgr.build(capi.make_nodes(qx, ql), qo)
     F = o.current_frame_id
     ref = None
-    for env in ({}, {"SGTD_VOTE_MODE": "stream"}, {"SGTD_JOIN_GROUPS": "3"}, {"SGTD_COLLECT_MODE": "desc"}):
-        for k in ("SGTD_VOTE_MODE", "SGTD_JOIN_GROUPS", "SGTD_COLLECT_MODE"):
-            monkeypatch.delenv(k, raising=False)
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
+    names = ("vote_stream", "join_groups", "collect_mode", "join_impl")
+    for opt in ({}, {"join_impl": 0}, {"join_impl": 2}, {"vote_stream": 1}, {"join_groups": 3},
+                {"join_groups": 3, "join_impl": 0}, {"join_groups": 5, "join_impl": 2}, {"collect_mode": 2}):
+        for k in names:
+            mgr.set_option(k, opt.get(k, 1 if k == "join_impl" else 0))
         res = mgr.search(qb)
         loops, cands = res.download()
         stats, _ = res.stats()
@@ -142,8 +145,10 @@ def test_vote_formulations_agree(world, built, monkeypatch):
         if ref is None:
             ref = cur
         else:
-            assert cur[0] == ref[0] and cur[1] == ref[1] and cur[3] == ref[3]
-            assert cur[2] == ref[2] and cur[4] == ref[4]
+            assert cur[0] == ref[0] and cur[1] == ref[1] and cur[3] == ref[3], opt
+            assert cur[2] == ref[2] and cur[4] == ref[4], opt
+    for k in names:
+        mgr.set_option(k, 1 if k == "join_impl" else 0)
 
 
 @pytest.mark.parametrize("over", [

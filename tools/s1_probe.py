@@ -1,15 +1,32 @@
-"""Stage-1 timing probe (debug helper): a batch of synthetic scans through sgtd_extract_instances_batch."""
-import os, sys, time
+"""Stage-1 timing probe (GPU box): a batch of labelled scans of the street sequence through
+sgtd_extract_instances_batch, device-resident inputs.  python tools/s1_probe.py [nscans] [reps]
+Run under `ncu --metrics gpu__time_duration.sum` for the per-kernel launch list."""
+import os
+import sys
+import time
+
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from sgtd_b200 import capi, synth_scan
-ns = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-base = [synth_scan.make_scan(5000 + s) for s in range(8)]
-scans = [base[s % 8] for s in range(ns)]
-off = np.concatenate([[0], np.cumsum([p.shape[0] for p, _ in scans])]).astype(np.int64)
-P = np.concatenate([p for p, _ in scans]); L = np.concatenate([l for _, l in scans])
-m = capi.STDescManager(device=0)
-for it in range(3):
-    t0 = time.perf_counter(); nodes, noff, pi, ninst = m.extract_instances(P, L, off); dt = time.perf_counter() - t0
-    print(f"gpu batch {ns} scans: {dt*1e3:.1f} ms -> {ns/dt:.1f} scans/s, nodes/scan {len(nodes)/ns:.1f}")
-t0 = time.perf_counter(); nodes, noff, pi, ninst = m.extract_instances(*base[0]); print("gpu single scan %.1f ms" % ((time.perf_counter()-t0)*1e3))
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sgtd_b200 import capi, synth, synth_seq  # noqa: E402
+
+nscans = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+dev = torch.device("cuda", 0)
+w = synth_seq.make_street_world(4541, synth.BASE_SEED + 1)
+sel = np.linspace(0, 4540, nscans).astype(int)
+pts, labs, off = [], [], [0]
+for i in sel:
+    p, l = synth_seq.render_at(w, w["poses"][i], 10_000 + int(i), device=dev)
+    pts.append(p); labs.append(l.to(torch.int32)); off.append(off[-1] + p.shape[0])
+pts, labs, off = torch.cat(pts).contiguous(), torch.cat(labs).contiguous(), np.array(off, np.int64)
+mgr = capi.STDescManager(device=0)
+for it in range(reps):
+    mgr.set_option("s1_trace", 1 if it == reps - 1 and os.environ.get("S1_TRACE") else 0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nodes, noff, ninst = mgr.extract_instances_ptr(pts.data_ptr(), labs.data_ptr(), off)
+    torch.cuda.synchronize()
+    print(f"rep {it}: {1e3 * (time.perf_counter() - t0):.2f} ms for {nscans} scans, {int(off[-1])} points, {len(nodes)} nodes", flush=True)
