@@ -323,6 +323,41 @@ int sgtd_recall_rank(const sgtd_candidate *cands, int32_t ncand, const double *m
                      int64_t n_map, const double *gt12, double radius, int32_t *rank,
                      int32_t *order);
 
+/* ---- GICP refinement of the verified candidates (the reference's final method) ------ */
+/* Parameters of fast_gicp::FastGICP as the node sets them (R/src/semantic_graph_localization.cpp:223-237,
+ * 664-669; R/config/SG_localization.yaml:15,24-25; defaults of lsq_registration_impl.hpp:9-21). */
+typedef struct sgtd_gicp_params {
+  int32_t num_neighbors;         /* setCorrespondenceRandomness: k of the covariance neighbourhoods (20) */
+  int32_t max_iterations;        /* setMaximumIterations (10)                                             */
+  double rotation_epsilon;       /* 2e-3                                                                  */
+  double transformation_epsilon; /* 5e-4                                                                  */
+  double best_fitness;           /* SG_data/best_fitness: a candidate below it ends the search (15)       */
+  int32_t reuse_target;          /* 1: keep the target's covariances while the same target buffer is passed */
+  int32_t reserved;
+} sgtd_gicp_params;
+int sgtd_gicp_params_default(sgtd_gicp_params *p);
+/* FastGICP::align on one (source, target) pair, as the node calls it (:692-703): the source (n x 3 floats,
+ * already down-sampled) is first moved by init12 (row-major 3x4, the candidate's loop transform; NULL =
+ * identity) in float, then aligned to the target with the identity guess: per-point covariances from the
+ * num_neighbors nearest neighbours with PLANE regularisation, Levenberg-Marquardt on the
+ * distribution-to-distribution cost.  final12 = reg.getFinalTransformation() (3x4, the values of the float
+ * matrix), *fitness = reg.getFitnessScore() (mean squared nearest-neighbour distance of the aligned source).
+ * Clouds may be host or device memory.  Floating point: agrees with the CPU restatement within
+ * 1e-6 (transform) / 1e-6 relative (fitness), see tests/test_gpu_gicp.py. */
+int sgtd_gicp_align(sgtd_handle *h, const float *source_xyz, int64_t n_source, const float *target_xyz,
+                    int64_t n_target, const double *init12, const sgtd_gicp_params *params,
+                    double *final12, double *fitness, int32_t *iterations, int32_t *converged);
+/* The node's multi-candidate loop (:603, :651-721): candidates are visited in `order` (match_fitness
+ * descending, e.g. from sgtd_recall_rank; NULL = as given), each is aligned against its own target cloud
+ * targets_xyz[c] (NULL = skip); the lowest fitness below 100 wins and the first one below
+ * params->best_fitness ends the search.  *chosen = -1 if none.  transformation12 = the winner's
+ * getFinalTransformation (the `transformation` of the success test, see sgtd_localization_check). */
+int sgtd_gicp_refine_candidates(sgtd_handle *h, const float *source_xyz, int64_t n_source,
+                                const float *const *targets_xyz, const int64_t *n_targets,
+                                const sgtd_candidate *cands, const int32_t *order, int32_t ncand,
+                                const sgtd_gicp_params *params, int32_t *chosen, double *transformation12,
+                                double *fitness, int32_t *n_aligned);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,9 @@ def lib():
         L.orc_extract_instances.restype = C.c_int32
         L.orc_extract_instances.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.orc_gicp_align.restype = C.c_int32
+        L.orc_gicp_align.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -229,3 +232,18 @@ def extract_instances(points, labels):
     k = nn.value
     return dict(point_instance=pi, node_xyz=nx[:k].copy(), node_label=nl[:k].copy(), node_inst=ni[:k].copy(),
                 n_instances=ninst.value)
+
+
+def gicp_align(source, target, init12=None, k=20, max_iterations=10, rot_eps=2e-3, trans_eps=5e-4):
+    """fast_gicp::FastGICP::align as the node calls it -> (final 4x4, fitness, iterations, converged)."""
+    source = np.ascontiguousarray(source, np.float32).reshape(-1, 3)
+    target = np.ascontiguousarray(target, np.float32).reshape(-1, 3)
+    init = np.eye(4)[:3].reshape(12).copy() if init12 is None else np.ascontiguousarray(init12, np.float64).reshape(12)
+    fin = np.zeros(16)
+    fit = C.c_double(0)
+    it, cv = C.c_int32(0), C.c_int32(0)
+    rc = lib().orc_gicp_align(_p(source), source.shape[0], _p(target), target.shape[0], _p(init), k, max_iterations,
+                              rot_eps, trans_eps, _p(fin), C.byref(fit), C.byref(it), C.byref(cv))
+    if rc:
+        raise ValueError("orc_gicp_align: clouds smaller than k")
+    return fin.reshape(4, 4), fit.value, it.value, bool(cv.value)

@@ -41,6 +41,12 @@ class Config(C.Structure):
         ("icp_threshold", C.c_double), ("normal_threshold", C.c_double), ("dis_threshold", C.c_double)]
 
 
+class GicpParams(C.Structure):
+    _fields_ = [("num_neighbors", C.c_int32), ("max_iterations", C.c_int32), ("rotation_epsilon", C.c_double),
+                ("transformation_epsilon", C.c_double), ("best_fitness", C.c_double), ("reuse_target", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class VoteStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("Q", "P", "Pfound", "E", "M", "B", "Eu")]
 
@@ -96,6 +102,9 @@ SYMBOLS = {
     "sgtd_scan_read_kitti": (C.c_int, [C.c_char_p, C.c_char_p, _VP, _VP, _I64, _VP]),
     "sgtd_pose_error": (C.c_int, [_VP, _VP, _VP, _VP]),
     "sgtd_localization_check": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP]),
+    "sgtd_gicp_params_default": (C.c_int, [C.POINTER(GicpParams)]),
+    "sgtd_gicp_align": (C.c_int, [_VP, _VP, _I64, _VP, _I64, _VP, C.POINTER(GicpParams), _VP, _VP, _VP, _VP]),
+    "sgtd_gicp_refine_candidates": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP, _I32, C.POINTER(GicpParams), _VP, _VP, _VP, _VP]),
     "sgtd_set_option": (C.c_int, [_VP, C.c_char_p, C.c_int32]),
     "sgtd_recall_rank": (C.c_int, [_VP, C.c_int32, _VP, C.c_int64, _VP, C.c_double, _VP, _VP]),
 }
@@ -293,6 +302,44 @@ class STDescManager:
     @property
     def stream(self):
         return int(lib().sgtd_stream(self._h) or 0)
+
+    # -- GICP refinement (fast_gicp::FastGICP as the node uses it) ---------------------------------
+    def gicp_params(self, **over):
+        p = GicpParams()
+        self._chk(lib().sgtd_gicp_params_default(C.byref(p)))
+        for k, v in over.items():
+            setattr(p, k, v)
+        return p
+
+    def gicp_align(self, source, target, init12=None, params=None):
+        """-> (final 3x4, fitness, iterations, converged)"""
+        source = np.ascontiguousarray(source, np.float32).reshape(-1, 3)
+        target = np.ascontiguousarray(target, np.float32).reshape(-1, 3)
+        p = params or self.gicp_params()
+        init = None if init12 is None else np.ascontiguousarray(init12, np.float64).reshape(12)
+        fin = np.zeros(12)
+        fit = C.c_double(0)
+        it, cv = C.c_int32(0), C.c_int32(0)
+        self._chk(lib().sgtd_gicp_align(self._h, _p(source), source.shape[0], _p(target), target.shape[0], _p(init),
+                                        C.byref(p), _p(fin), C.byref(fit), C.byref(it), C.byref(cv)))
+        return fin.reshape(3, 4), fit.value, it.value, bool(cv.value)
+
+    def gicp_refine_candidates(self, source, targets, cands, order=None, params=None):
+        """the node's multi-candidate loop -> (chosen candidate or -1, transformation 3x4, fitness, n_aligned)"""
+        source = np.ascontiguousarray(source, np.float32).reshape(-1, 3)
+        cands = np.ascontiguousarray(cands, CAND_DTYPE)
+        n = len(cands)
+        keep = [None if t is None else np.ascontiguousarray(t, np.float32).reshape(-1, 3) for t in targets]
+        ptrs = (C.c_void_p * n)(*[None if t is None else t.ctypes.data for t in keep])
+        sizes = np.array([0 if t is None else t.shape[0] for t in keep], np.int64)
+        order = None if order is None else np.ascontiguousarray(order, np.int32)
+        p = params or self.gicp_params()
+        chosen, nal = C.c_int32(-1), C.c_int32(0)
+        T = np.zeros(12)
+        fit = C.c_double(0)
+        self._chk(lib().sgtd_gicp_refine_candidates(self._h, _p(source), source.shape[0], ptrs, _p(sizes), _p(cands), _p(order), n,
+                                                    C.byref(p), C.byref(chosen), _p(T), C.byref(fit), C.byref(nal)))
+        return chosen.value, T.reshape(3, 4), fit.value, nal.value
 
     def set_option(self, name, value):
         """experiment / parity switches (sgtd_set_option): vote_stream, join_groups, collect_mode, ..."""

@@ -249,6 +249,7 @@ int sgtd_destroy(sgtd_handle *h) {
   h->v_s0.release(); h->v_s1.release(); h->v_s2.release(); h->v_frame.release(); h->v_pack.release(); h->v_pack8.release();
   h->table.release(); h->f_key.release(); h->f_g.release(); h->f_side.release(); h->scratch.release(); h->stage_in.release(); h->uniq_bitmap.release();
   if (h->s1pool && h->s1pool_free) h->s1pool_free(h->s1pool);
+  if (h->gicp_pool && h->gicp_pool_free) h->gicp_pool_free(h->gicp_pool);
   for (auto *r : h->result_pool) destroy_result(r);
   for (auto *b : h->batch_pool) destroy_batch(b);
   for (auto *r : h->live_results) release_result(r);  // orphaned: the caller's free() just deletes

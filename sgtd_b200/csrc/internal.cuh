@@ -192,6 +192,8 @@ struct sgtd_handle {
   std::unordered_set<sgtd_desc_batch *> live_batches;
   void *s1pool = nullptr;                 // stage-1 temporaries (instances.cu)
   void (*s1pool_free)(void *) = nullptr;
+  void *gicp_pool = nullptr;              // GICP temporaries (gicp.cu)
+  void (*gicp_pool_free)(void *) = nullptr;
   int64_t frame_lo() const { return frames_per_rank ? (int64_t)rank * frames_per_rank : 0; }
   int64_t frames_local() const { return (int64_t)frame_off.size() - 1; }
 };
