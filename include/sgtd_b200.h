@@ -170,7 +170,9 @@ int64_t sgtd_kernel_launches(const sgtd_handle *h);   /* kernels launched so far
 /* Behaviour switches for experiments and parity tests.  They never change results, only which
  * kernel formulation runs: "vote_stream" (1 = the per-probe streaming vote kernel, exact FP64 on every
  * entry, instead of the bucket-major join), "join_groups" (query groups of the join, 0 = automatic),
- * "collect_mode" (0 auto, 1 inverted, 2 per-descriptor), "collect_group", "debug_novote".  The same
+ * "collect_mode" (0 auto, 1 inverted, 2 per-descriptor), "collect_group", "debug_novote",
+ * "join_impl" (1 default; 0 / 2 experimental joins on 8-byte entries), "stats_unique", "s1_trace";
+ * "s1_variant" (1 = class tables of local_map_creation) is the one that selects behaviour.  The same
  * switches are read once from the environment by sgtd_create (SGTD_VOTE_MODE=stream, SGTD_JOIN_GROUPS,
  * SGTD_COLLECT_MODE=desc|inv, SGTD_COLLECT_GROUP, SGTD_DEBUG_NOVOTE); sgtd_search never reads the
  * environment. */
@@ -322,6 +324,23 @@ int sgtd_localization_check(const double *map_pose12, const double *R9, const do
 int sgtd_recall_rank(const sgtd_candidate *cands, int32_t ncand, const double *map_poses12,
                      int64_t n_map, const double *gt12, double radius, int32_t *rank,
                      int32_t *order);
+
+/* ---- submap aggregation (R/src/local_map.cpp:213-486) ----------------------------- */
+/* The point-gathering part of local_map_creation (:213-328), literally: the scan's own points
+ * (n x float4 x,y,z,intensity + labels), then one transformed copy
+ * T_j^-1 * T_i * BASE2OUSTER * p for every other scan i of the submap whose translation lies
+ * within `radius` (15 m) of scan j's.  Reference quirks kept: every copy is made of the CURRENT
+ * scan's points (the reference re-opens current_scan_path for each neighbour, :272), the intensity
+ * acts as the homogeneous coordinate, and the scan's last point enters the copies as (1,1,1,1)
+ * (:290).  poses12: nscans row-major 3x4 float poses; base2ouster16: row-major 4x4 (NULL =
+ * identity).  Buffers may be host or device memory; *n_out is set even on SGTD_E_CAPACITY.  Float
+ * arithmetic (tests/test_submap.py states the tolerance).  The instance extraction that follows
+ * (:330-486) is sgtd_extract_instances[_batch] with option "s1_variant" = 1 (its class tables:
+ * class 19 not skipped, minSeg 400 for classes 10,11,12,14,16). */
+int sgtd_submap_aggregate(sgtd_handle *h, const float *points, const uint32_t *labels, int64_t n,
+                          const float *poses12, int32_t nscans, int32_t j,
+                          const float *base2ouster16, float radius, float *out_points,
+                          uint32_t *out_labels, int64_t cap, int64_t *n_out, int32_t *n_used);
 
 /* ---- GICP refinement of the verified candidates (the reference's final method) ------ */
 /* Parameters of fast_gicp::FastGICP as the node sets them (R/src/semantic_graph_localization.cpp:223-237,

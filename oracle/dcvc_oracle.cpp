@@ -212,9 +212,9 @@ int32_t orc_dcvc(const float *xyz, int64_t n, double startR, double deltaR, doub
  * point_instance[n]: instance id of each point, -1 if the point is in no instance.
  * node_xyz[cap*3], node_label[cap], node_inst[cap] (instance id of each node).
  * Returns 0, or -2 if cap_nodes is too small. */
-int32_t orc_extract_instances(const float *points, const uint32_t *labels, int64_t n, int32_t *point_instance,
-                              float *node_xyz, uint32_t *node_label, int32_t *node_inst, int32_t cap_nodes,
-                              int32_t *n_nodes, int32_t *n_instances) {
+static int32_t extract_instances_impl(const float *points, const uint32_t *labels, int64_t n, int32_t *point_instance,
+                                      float *node_xyz, uint32_t *node_label, int32_t *node_inst, int32_t cap_nodes,
+                                      int32_t *n_nodes, int32_t *n_instances, int variant) {
   std::vector<int> sem((size_t)n), ins((size_t)n);
   for (int64_t i = 0; i < n; ++i) {
     int lab = (int)labels[i];
@@ -237,7 +237,8 @@ int32_t orc_extract_instances(const float *points, const uint32_t *labels, int64
       inst_id += 1;
       continue;
     } else if (label_i == 0 || label_i == 1 || label_i == 2 || label_i == 3 || label_i == 6 || label_i == 7 ||
-               label_i == 8 || label_i == 14 || label_i == 19) { /* :137 */
+               label_i == 8 || label_i == 14 || (label_i == 19 && variant == 0)) {
+      /* get_json.cpp:137; local_map.cpp:388 has the same list without 19 */
       continue;
     } else if (inst_set.size() > 1 || (inst_set.size() == 1 && *inst_set.begin() != 0)) { /* :138-159 */
       for (int label_j : inst_set) {
@@ -251,6 +252,8 @@ int32_t orc_extract_instances(const float *points, const uint32_t *labels, int64
     } else { /* :160-226 */
       int DCVC_min = 300;
       if (label_i == 17 || label_i == 18 || label_i == 15) DCVC_min = 5;
+      /* local_map_creation (local_map.cpp:412-440): 400 for the large-surface classes */
+      if (variant == 1 && (label_i == 10 || label_i == 11 || label_i == 12 || label_i == 14 || label_i == 16)) DCVC_min = 400;
       ClusterManager cm;
       cm.params_ = DcvcParams{0.35, 0.0004, 1.2, 1.2, DCVC_min};
       std::vector<std::array<float, 3>> cloud;
@@ -293,6 +296,92 @@ int32_t orc_extract_instances(const float *points, const uint32_t *labels, int64
   }
   *n_nodes = nn;
   return 0;
+}
+
+int32_t orc_extract_instances(const float *points, const uint32_t *labels, int64_t n, int32_t *point_instance,
+                              float *node_xyz, uint32_t *node_label, int32_t *node_inst, int32_t cap_nodes,
+                              int32_t *n_nodes, int32_t *n_instances) {
+  return extract_instances_impl(points, labels, n, point_instance, node_xyz, node_label, node_inst, cap_nodes, n_nodes,
+                                n_instances, 0);
+}
+/* the same with the class tables of local_map_creation (R/src/local_map.cpp:384-440) */
+int32_t orc_extract_instances_submap(const float *points, const uint32_t *labels, int64_t n, int32_t *point_instance,
+                                     float *node_xyz, uint32_t *node_label, int32_t *node_inst, int32_t cap_nodes,
+                                     int32_t *n_nodes, int32_t *n_instances) {
+  return extract_instances_impl(points, labels, n, point_instance, node_xyz, node_label, node_inst, cap_nodes, n_nodes,
+                                n_instances, 1);
+}
+
+/* The point-gathering part of local_map_creation (R/src/local_map.cpp:213-328), literally:
+ * the scan's own points, then for every OTHER scan i of the submap whose translation lies within 15 m
+ * (`(t1-t2).norm() > 15` skips) one transformed copy  T_j^-1 * T_i * BASE2OUSTER * p  -- of the CURRENT
+ * scan's points again (the reference re-opens current_scan_path / current_label_path for every
+ * neighbour, :272,:301), with the 4th component of each point (the intensity) acting as the homogeneous
+ * coordinate except for the scan's last point, whose four components are set to one (:290 sets the last
+ * COLUMN).  poses: nscans x 12 floats (row-major 3x4); b2o16: row-major 4x4.  Float arithmetic; the 4x4
+ * inverse and products are Eigen's in the reference (order restated: cofactor inverse, k = 0..3 sums).
+ * Returns the number of output points (n * copies), or -1 if cap is too small. */
+static void mul44f(const float *a, const float *b, float *c) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float v = a[i * 4] * b[j];
+      v += a[i * 4 + 1] * b[4 + j];
+      v += a[i * 4 + 2] * b[8 + j];
+      v += a[i * 4 + 3] * b[12 + j];
+      c[i * 4 + j] = v;
+    }
+}
+static void inv_rigid44f(const float *m, float *o) { /* general 4x4 with last row (0,0,0,1): cofactors of the 3x3 block */
+  const float c00 = m[5] * m[10] - m[6] * m[9], c01 = m[6] * m[8] - m[4] * m[10], c02 = m[4] * m[9] - m[5] * m[8];
+  const float det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  const float id = 1.0f / det;
+  float r[9];
+  r[0] = c00 * id; r[1] = (m[2] * m[9] - m[1] * m[10]) * id; r[2] = (m[1] * m[6] - m[2] * m[5]) * id;
+  r[3] = c01 * id; r[4] = (m[0] * m[10] - m[2] * m[8]) * id; r[5] = (m[2] * m[4] - m[0] * m[6]) * id;
+  r[6] = c02 * id; r[7] = (m[1] * m[8] - m[0] * m[9]) * id; r[8] = (m[0] * m[5] - m[1] * m[4]) * id;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) o[i * 4 + j] = r[i * 3 + j];
+    o[i * 4 + 3] = -((r[i * 3] * m[3] + r[i * 3 + 1] * m[7]) + r[i * 3 + 2] * m[11]);
+  }
+  o[12] = o[13] = o[14] = 0.0f; o[15] = 1.0f;
+}
+int64_t orc_submap_aggregate(const float *points, const uint32_t *labels, int64_t n, const float *poses, int32_t nscans,
+                             int32_t j, const float *b2o16, float radius, float *out_points, uint32_t *out_labels,
+                             int64_t cap, int32_t *n_used) {
+  auto pose44 = [&](int s, float *m) { for (int k = 0; k < 12; ++k) m[k] = poses[(size_t)s * 12 + k]; m[12] = m[13] = m[14] = 0.0f; m[15] = 1.0f; };
+  float Tj[16], Tji[16];
+  pose44(j, Tj);
+  inv_rigid44f(Tj, Tji);
+  int used = 1;
+  int64_t o = 0;
+  if (n > cap) return -1;
+  for (int64_t p = 0; p < n; ++p) { for (int k = 0; k < 4; ++k) out_points[4 * o + k] = points[4 * p + k]; out_labels[o] = labels[p]; ++o; }
+  for (int i = 0; i < nscans; ++i) {
+    if (i == j) continue;
+    const float dx = Tj[3] - poses[(size_t)i * 12 + 3], dy = Tj[7] - poses[(size_t)i * 12 + 7], dz = Tj[11] - poses[(size_t)i * 12 + 11];
+    if (std::sqrt(dx * dx + (dy * dy + dz * dz)) > radius) continue; /* Eigen Vector3f::norm() */
+    ++used;
+    if (o + n > cap) return -1;
+    float Ti[16], A[16], T[16];
+    pose44(i, Ti);
+    mul44f(Tji, Ti, A);
+    mul44f(A, b2o16, T);
+    for (int64_t p = 0; p < n; ++p) {
+      float v[4] = {points[4 * p], points[4 * p + 1], points[4 * p + 2], points[4 * p + 3]};
+      if (p == n - 1) v[0] = v[1] = v[2] = v[3] = 1.0f; /* points.col(points.cols() - 1).setOnes() */
+      for (int r = 0; r < 4; ++r) {
+        float acc = T[r * 4] * v[0];
+        acc += T[r * 4 + 1] * v[1];
+        acc += T[r * 4 + 2] * v[2];
+        acc += T[r * 4 + 3] * v[3];
+        out_points[4 * o + r] = acc;
+      }
+      out_labels[o] = labels[p];
+      ++o;
+    }
+  }
+  if (n_used) *n_used = used;
+  return o;
 }
 
 } /* extern "C" */

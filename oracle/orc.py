@@ -77,6 +77,11 @@ def lib():
         L.orc_extract_instances.restype = C.c_int32
         L.orc_extract_instances.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.orc_extract_instances_submap.restype = C.c_int32
+        L.orc_extract_instances_submap.argtypes = L.orc_extract_instances.argtypes
+        L.orc_submap_aggregate.restype = C.c_int64
+        L.orc_submap_aggregate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                           C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_gicp_align.restype = C.c_int32
         L.orc_gicp_align.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -212,8 +217,25 @@ def dcvc(xyz, startR=0.35, deltaR=0.0004, deltaP=1.2, deltaA=1.2, minSeg=300):
     return lab, cl, int(nc), tuple(int(x) for x in grid)
 
 
-def extract_instances(points, labels):
-    """gen_labels + gen_graphs nodes.  points [n,4] float32, labels [n] uint32.
+def submap_aggregate(points, labels, poses12, j, b2o=None, radius=15.0):
+    """the point-gathering part of local_map_creation (R/src/local_map.cpp:213-328), literally.
+    -> (points [m,4], labels [m], scans used)"""
+    points = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
+    labels = np.ascontiguousarray(labels, np.uint32)
+    poses = np.ascontiguousarray(poses12, np.float32).reshape(-1, 12)
+    b = np.eye(4, dtype=np.float32) if b2o is None else np.ascontiguousarray(b2o, np.float32).reshape(4, 4)
+    cap = points.shape[0] * poses.shape[0]
+    op = np.zeros((cap, 4), np.float32)
+    ol = np.zeros(cap, np.uint32)
+    used = C.c_int32(0)
+    m = lib().orc_submap_aggregate(_p(points), _p(labels), points.shape[0], _p(poses), poses.shape[0], j, _p(b), radius,
+                                   _p(op), _p(ol), cap, C.byref(used))
+    return op[:m].copy(), ol[:m].copy(), used.value
+
+
+def extract_instances(points, labels, submap=False):
+    """gen_labels + gen_graphs nodes (submap=True: the class tables of local_map_creation).
+    points [n,4] float32, labels [n] uint32.
     Returns dict(point_instance[n], node_xyz[k,3], node_label[k], node_inst[k], n_instances)."""
     points = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
     labels = np.ascontiguousarray(labels, np.uint32)
@@ -225,8 +247,8 @@ def extract_instances(points, labels):
     ni = np.zeros(cap, np.int32)
     nn = C.c_int32(0)
     ninst = C.c_int32(0)
-    rc = lib().orc_extract_instances(_p(points), _p(labels), n, _p(pi), _p(nx), _p(nl), _p(ni), cap,
-                                     C.byref(nn), C.byref(ninst))
+    fn = lib().orc_extract_instances_submap if submap else lib().orc_extract_instances
+    rc = fn(_p(points), _p(labels), n, _p(pi), _p(nx), _p(nl), _p(ni), cap, C.byref(nn), C.byref(ninst))
     if rc:
         raise RuntimeError("orc_extract_instances: capacity")
     k = nn.value

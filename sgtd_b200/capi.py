@@ -102,6 +102,7 @@ SYMBOLS = {
     "sgtd_scan_read_kitti": (C.c_int, [C.c_char_p, C.c_char_p, _VP, _VP, _I64, _VP]),
     "sgtd_pose_error": (C.c_int, [_VP, _VP, _VP, _VP]),
     "sgtd_localization_check": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_double, C.c_double, _VP, _VP, _VP, _VP]),
+    "sgtd_submap_aggregate": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _I32, _I32, _VP, C.c_float, _VP, _VP, _I64, _VP, _VP]),
     "sgtd_gicp_params_default": (C.c_int, [C.POINTER(GicpParams)]),
     "sgtd_gicp_align": (C.c_int, [_VP, _VP, _I64, _VP, _I64, _VP, C.POINTER(GicpParams), _VP, _VP, _VP, _VP]),
     "sgtd_gicp_refine_candidates": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP, _I32, C.POINTER(GicpParams), _VP, _VP, _VP, _VP]),
@@ -302,6 +303,21 @@ class STDescManager:
     @property
     def stream(self):
         return int(lib().sgtd_stream(self._h) or 0)
+
+    def submap_aggregate(self, points, labels, poses12, j, b2o=None, radius=15.0):
+        """local_map_creation's point gathering (R/src/local_map.cpp:213-328) -> (points [m,4], labels [m], scans used)"""
+        points = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
+        labels = np.ascontiguousarray(labels, np.uint32)
+        poses = np.ascontiguousarray(poses12, np.float32).reshape(-1, 12)
+        b = None if b2o is None else np.ascontiguousarray(b2o, np.float32).reshape(16)
+        n_out, used = C.c_int64(0), C.c_int32(0)
+        lib().sgtd_submap_aggregate(self._h, _p(points), _p(labels), points.shape[0], _p(poses), poses.shape[0], j, _p(b),
+                                    radius, None, None, 0, C.byref(n_out), C.byref(used))
+        op = np.zeros((n_out.value, 4), np.float32)
+        ol = np.zeros(n_out.value, np.uint32)
+        self._chk(lib().sgtd_submap_aggregate(self._h, _p(points), _p(labels), points.shape[0], _p(poses), poses.shape[0], j,
+                                              _p(b), radius, _p(op), _p(ol), n_out.value, C.byref(n_out), C.byref(used)))
+        return op, ol, used.value
 
     # -- GICP refinement (fast_gicp::FastGICP as the node uses it) ---------------------------------
     def gicp_params(self, **over):

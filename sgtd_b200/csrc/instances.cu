@@ -765,10 +765,17 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
       if (!cnt) continue;
       Task t{};
       t.scan = s; t.cls = c; t.pt0 = off[s] - off[0]; t.npts_scan = (int)(off[s + 1] - off[s]); t.npts = (int)cnt;
+      // class tables: gen_labels (get_json.cpp:120-209) or, option s1_variant = 1, local_map_creation
+      // (local_map.cpp:372-440: class 19 is not skipped, minSeg 400 for the large-surface classes)
+      const bool submap = h->opt.s1_variant == 1;
       if (c == 9 || c == 10) t.policy = P_WHOLE;
-      else if (c == 0 || c == 1 || c == 2 || c == 3 || c == 6 || c == 7 || c == 8 || c == 14 || c == 19) continue;
+      else if (c == 0 || c == 1 || c == 2 || c == 3 || c == 6 || c == 7 || c == 8 || c == 14 || (c == 19 && !submap)) continue;
       else if (hc[(size_t)(nscans + s) * kMaxClass + c]) t.policy = P_GTINST;
-      else { t.policy = P_DCVC; t.minSeg = (c == 17 || c == 18 || c == 15) ? 5 : 300; }
+      else {
+        t.policy = P_DCVC;
+        t.minSeg = (c == 17 || c == 18 || c == 15) ? 5 : 300;
+        if (submap && (c == 10 || c == 11 || c == 12 || c == 14 || c == 16)) t.minSeg = 400;
+      }
       t.idx_off = n_idx; n_idx += cnt;
       t.lab_off = n_lab; n_lab += (t.policy == P_GTINST) ? 65536 : (t.policy == P_DCVC ? (int64_t)cnt + 1 : 1);
       if (t.policy == P_DCVC) {
@@ -1045,4 +1052,128 @@ extern "C" int sgtd_extract_instances(sgtd_handle *h, const float *points, const
   if (n_nodes) *n_nodes = (int32_t)noff[1];
   if (n_instances) *n_instances = ni;
   return SGTD_OK;
+}
+
+// ---- submap aggregation: the point-gathering part of local_map_creation -----------------
+// R/src/local_map.cpp:213-328, literally: the scan's own points, then one transformed copy per other scan of
+// the submap within `radius` of it -- of the CURRENT scan's points (the reference re-opens current_scan_path
+// for every neighbour, :272), the intensity acting as homogeneous coordinate except for the last point, whose
+// four components are one (:290).  A pure streaming transform: 16 B read (L2 after the first copy) and 20 B
+// written per output point.
+namespace sgtd {
+struct Mat44f { float m[16]; };
+__global__ void k_submap_copies(const float4 *pts, const uint32_t *lab, int64_t n, const Mat44f *T, int ncopies, float4 *out,
+                                uint32_t *out_lab) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float4 v0 = pts[p];
+  const uint32_t l = lab[p];
+  out[p] = v0; out_lab[p] = l;
+  float4 v = v0;
+  if (p == n - 1) v = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (int c = 0; c < ncopies; ++c) {
+    const float *m = T[c].m;
+    float4 o;
+    o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], v.x), __fmul_rn(m[1], v.y)), __fmul_rn(m[2], v.z)), __fmul_rn(m[3], v.w));
+    o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], v.x), __fmul_rn(m[5], v.y)), __fmul_rn(m[6], v.z)), __fmul_rn(m[7], v.w));
+    o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], v.x), __fmul_rn(m[9], v.y)), __fmul_rn(m[10], v.z)), __fmul_rn(m[11], v.w));
+    o.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[12], v.x), __fmul_rn(m[13], v.y)), __fmul_rn(m[14], v.z)), __fmul_rn(m[15], v.w));
+    out[(int64_t)(c + 1) * n + p] = o;
+    out_lab[(int64_t)(c + 1) * n + p] = l;
+  }
+}
+static void mul44f(const float *a, const float *b, float *c) {  // Matrix4f product, k = 0..3 in order
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float v = a[i * 4] * b[j];
+      v += a[i * 4 + 1] * b[4 + j];
+      v += a[i * 4 + 2] * b[8 + j];
+      v += a[i * 4 + 3] * b[12 + j];
+      c[i * 4 + j] = v;
+    }
+}
+static void inv44f(const float *m, float *o) {  // last row (0,0,0,1): cofactors of the 3x3 block
+  const float c00 = m[5] * m[10] - m[6] * m[9], c01 = m[6] * m[8] - m[4] * m[10], c02 = m[4] * m[9] - m[5] * m[8];
+  const float id = 1.0f / (m[0] * c00 + m[1] * c01 + m[2] * c02);
+  float r[9];
+  r[0] = c00 * id; r[1] = (m[2] * m[9] - m[1] * m[10]) * id; r[2] = (m[1] * m[6] - m[2] * m[5]) * id;
+  r[3] = c01 * id; r[4] = (m[0] * m[10] - m[2] * m[8]) * id; r[5] = (m[2] * m[4] - m[0] * m[6]) * id;
+  r[6] = c02 * id; r[7] = (m[1] * m[8] - m[0] * m[9]) * id; r[8] = (m[0] * m[5] - m[1] * m[4]) * id;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) o[i * 4 + j] = r[i * 3 + j];
+    o[i * 4 + 3] = -((r[i * 3] * m[3] + r[i * 3 + 1] * m[7]) + r[i * 3 + 2] * m[11]);
+  }
+  o[12] = o[13] = o[14] = 0.0f; o[15] = 1.0f;
+}
+}  // namespace sgtd
+
+extern "C" int sgtd_submap_aggregate(sgtd_handle *h, const float *points, const uint32_t *labels, int64_t n,
+                                     const float *poses12, int32_t nscans, int32_t j, const float *base2ouster16,
+                                     float radius, float *out_points, uint32_t *out_labels, int64_t cap, int64_t *n_out,
+                                     int32_t *n_used) {
+  if (!h || !points || !labels || !poses12 || !n_out || n < 0 || nscans < 1 || j < 0 || j >= nscans)
+    return sgtd_fail(h, SGTD_E_INVALID, "bad argument", __FILE__, __LINE__);
+  float Tj[16], Tji[16], I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  auto pose44 = [&](int s, float *m) { for (int k = 0; k < 12; ++k) m[k] = poses12[(size_t)s * 12 + k]; m[12] = m[13] = m[14] = 0.0f; m[15] = 1.0f; };
+  pose44(j, Tj);
+  inv44f(Tj, Tji);
+  const float *B = base2ouster16 ? base2ouster16 : I;
+  std::vector<Mat44f> Ts;
+  for (int i = 0; i < nscans; ++i) {
+    if (i == j) continue;
+    const float dx = Tj[3] - poses12[(size_t)i * 12 + 3], dy = Tj[7] - poses12[(size_t)i * 12 + 7], dz = Tj[11] - poses12[(size_t)i * 12 + 11];
+    if (sqrtf(dx * dx + (dy * dy + dz * dz)) > radius) continue;  // (t1 - t2).norm() > 15 (:268)
+    float Ti[16], A[16];
+    Mat44f T;
+    pose44(i, Ti);
+    mul44f(Tji, Ti, A);  // T_j.inverse() * T_i * BASE2OUSTER (:292)
+    mul44f(A, B, T.m);
+    Ts.push_back(T);
+  }
+  const int64_t total = n * (int64_t)(Ts.size() + 1);
+  *n_out = total;
+  if (n_used) *n_used = (int32_t)Ts.size() + 1;
+  if (!out_points || !out_labels || total > cap) return total > cap ? SGTD_E_CAPACITY : SGTD_OK;
+  if (total == 0) return SGTD_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(h->device);
+  cudaStream_t st = h->stream;
+  S1Pool &sp = s1_pool(h);
+  int rc = SGTD_OK;
+  cudaError_t e = cudaSuccess;
+  const bool in_dev = s1_is_device_ptr(points), out_dev = s1_is_device_ptr(out_points);
+  const float4 *d_pts = reinterpret_cast<const float4 *>(points);
+  const uint32_t *d_lab = labels;
+  DevBuf<float4> d_out; DevBuf<uint32_t> d_outl; DevBuf<Mat44f> d_T;
+  do {
+    if (!in_dev) {
+      if ((e = sp.in_pts.reserve((size_t)n, st, false)) != cudaSuccess) break;
+      if ((e = sp.in_lab.reserve((size_t)n, st, false)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(sp.in_pts.p, points, (size_t)n * 16, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(sp.in_lab.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+      d_pts = sp.in_pts.p; d_lab = sp.in_lab.p;
+    }
+    float4 *o_pts = reinterpret_cast<float4 *>(out_points);
+    uint32_t *o_lab = out_labels;
+    if (!out_dev) {
+      if ((e = d_out.reserve((size_t)total, st, false)) != cudaSuccess) break;
+      if ((e = d_outl.reserve((size_t)total, st, false)) != cudaSuccess) break;
+      o_pts = d_out.p; o_lab = d_outl.p;
+    }
+    if ((e = d_T.reserve(std::max<size_t>(Ts.size(), 1), st, false)) != cudaSuccess) break;
+    if (!Ts.empty() && (e = cudaMemcpyAsync(d_T.p, Ts.data(), Ts.size() * sizeof(Mat44f), cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    k_submap_copies<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_pts, d_lab, n, d_T.p, (int)Ts.size(), o_pts, o_lab);
+    SGTD_LAUNCHED(h);
+    if ((e = cudaGetLastError()) != cudaSuccess) break;
+    if (!out_dev) {
+      if ((e = cudaMemcpyAsync(out_points, o_pts, (size_t)total * 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+      if ((e = cudaMemcpyAsync(out_labels, o_lab, (size_t)total * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+    }
+    e = cudaStreamSynchronize(st);
+  } while (false);
+  if (e != cudaSuccess) rc = sgtd_fail(h, SGTD_E_CUDA, "sgtd_submap_aggregate", __FILE__, __LINE__, e);
+  d_out.release(); d_outl.release(); d_T.release();
+  if (prev >= 0 && prev != h->device) cudaSetDevice(prev);
+  return rc;
 }
