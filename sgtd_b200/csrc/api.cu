@@ -237,6 +237,8 @@ int sgtd_set_option(sgtd_handle *h, const char *name, int32_t value) {
   else if (!strcmp(name, "stats_unique")) h->opt.stats_unique = value != 0;
   else if (!strcmp(name, "s1_trace")) h->opt.s1_trace = value != 0;
   else if (!strcmp(name, "s1_variant")) h->opt.s1_variant = value == 1;
+  else if (!strcmp(name, "s1_rows")) h->opt.s1_rows = value != 0;
+  else if (!strcmp(name, "s1_table")) h->opt.s1_table = value == 1;
   else SGTD_FAIL(h, SGTD_E_INVALID, "unknown option");
   return SGTD_OK;
 }

@@ -299,6 +299,8 @@ __device__ __forceinline__ int uf_find_ro(const int *parent, int x) {
 constexpr int kRpThreads = 128;
 constexpr int kUfCap = 1024;     // union-find entries in shared memory; beyond: the task's global array
 constexpr int kRing = 256;       // events in the ring (two chunks of 128)
+constexpr int kRowRing = 128;    // neighbour rows kept ahead of the replaying warp
+constexpr int kProducers = kRpThreads / 32 - 1;
 constexpr uint32_t kVEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kCoordMask = 0x07FFFFFFu;  // az:9 | polar:10 | pitch:8
 
@@ -338,18 +340,18 @@ struct VoxTable {
   __device__ __forceinline__ int kind(int slot) const { return kSmem ? (int)(w[slot] >> 27) & 3 : __ldcg(t_kind + slot); }
   __device__ __forceinline__ void set(int slot, int kind, int label) {
     if (kSmem) { w[slot] = (w[slot] & kCoordMask) | ((uint32_t)kind << 27); lab[slot] = (uint16_t)label; }
-    else { t_kind[slot] = kind; t_label[slot] = label; }
+    else { __stcg(t_kind + slot, kind); __stcg(t_label + slot, label); }
   }
   __device__ __forceinline__ void set_kind(int slot, int kind) {
     if (kSmem) w[slot] = (w[slot] & kCoordMask) | ((uint32_t)kind << 27);
-    else t_kind[slot] = kind;
+    else __stcg(t_kind + slot, kind);
   }
 };
 
 struct UnionFind2 {
   int *sm, *gl;
   __device__ __forceinline__ int get(int x) const { return x < kUfCap ? sm[x] : __ldcg(gl + x); }
-  __device__ __forceinline__ void set(int x, int v) { if (x < kUfCap) sm[x] = v; else gl[x] = v; }
+  __device__ __forceinline__ void set(int x, int v) { if (x < kUfCap) sm[x] = v; else __stcg(gl + x, v); }
   // read-mostly find with path halving; concurrent callers only ever move pointers towards the root
   __device__ __forceinline__ int find(int x) {
     while (true) {
@@ -365,11 +367,14 @@ struct UnionFind2 {
 // nvox_lo < nvox <= nvox_hi selects the tasks of this launch (kSmem: table of `slots` entries in dynamic
 // shared memory); seeds that can create more labels than a 16-bit label holds go to the global form.
 template <bool kSmem>
-__global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slots, int nvox_lo, int nvox_hi) {
+__global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slots, int nvox_lo, int nvox_hi, int use_rows) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ int s_parent[kUfCap];
   __shared__ uint32_t s_stamp[kUfCap];  // per root: (event number << 5 | 31 - lowest lane that saw it in that event)
   __shared__ int2 s_ring[kRing];
+  __shared__ int s_rows[kRowRing][32];      // neighbour slots of upcoming events, produced by warps 1..3
+  __shared__ volatile int s_done[kRpThreads / 32];  // per producer warp: its events below this index are ready
+  __shared__ volatile int s_cpos;           // the replaying warp's position in the event list
   const Task t = B.tasks[blockIdx.x];
   if (t.policy != P_DCVC) return;
   const TaskState ts = B.ts[blockIdx.x];
@@ -415,11 +420,48 @@ __global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slo
     const int vis = (c >> 21) <= height;
     evc[e] = make_int2(slot | (ev.w << 28) | (vis << 30), ev.x);
   }
+  if (tid < kRpThreads / 32) s_done[tid] = 0;
+  if (tid == 0) s_cpos = 0;
   __threadfence_block();
   __syncthreads();
-  // ---- 3. sequential replay by warp 0
+  // ---- 3. sequential replay by warp 0; warps 1..3 run ahead of it and look the 27 neighbour voxels of every
+  //         event up (that part only depends on the table's keys, not on the labelling state)
   const long long c2 = clock64();
   int labelCount = 0, n_active = 0, n_windows = 0;
+  // neighbour k = lane of the voxel in `slot` (searchKNN order, :365-385); -1 = skipped by the guards or absent
+  auto neighbour = [&](int slot) -> int {
+    int az, po, pi;
+    if (kSmem) { const uint32_t c = T.w[slot] & kCoordMask; az = c & 511; po = (c >> 9) & 1023; pi = c >> 19; }
+    else { const int c = __ldcg(g_coord + slot); az = c & 1023; po = (c >> 10) & 2047; pi = c >> 21; }
+    int nb = -1;
+    if (lane < 27) {
+      const int z = pi - 1 + lane / 9, y = po - 1 + (lane / 3) % 3, x = az - 1 + lane % 3;
+      if (!(z < 0 || z > height) && !(y < 0 || y > polarNum)) {
+        int ax = x;
+        if (ax < 0) ax = width - 1;
+        if (ax > 300) ax = 300;
+        if (y < polarNum) nb = T.lookup(ax, y, z);  // polar index polarNum is legal for the guard but never occupied
+      }
+    }
+    return nb;
+  };
+  if (tid >= 32 && use_rows) {
+    const int hw = tid >> 5;  // producer warp hw takes the events e with e % kProducers == hw - 1
+    for (int e_base = hw - 1; e_base < nev; e_base += 32 * kProducers) {
+      const int mine_e = e_base + lane * kProducers;
+      const int2 mine = mine_e < nev ? evc[mine_e] : make_int2(0, 0);  // 32 events of this warp at a time
+      for (int j = 0; j < 32; ++j) {
+        const int e = e_base + j * kProducers;
+        if (e >= nev) break;
+        while (e >= s_cpos + kRowRing) __nanosleep(40);  // do not overwrite rows the replaying warp still needs
+        const int slot = __shfl_sync(0xffffffffu, mine.x, j) & 0x0FFFFFFF;
+        const int nb = neighbour(slot);
+        s_rows[e & (kRowRing - 1)][lane] = nb;
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); s_done[hw] = e + 1; }
+      }
+    }
+  }
   if (tid < 32) {
     UnionFind2 uf{s_parent, B.parent + t.lab_off};
     int loaded = 0, pre_base = 0;
@@ -451,27 +493,26 @@ __global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slo
       }
       const unsigned act = __ballot_sync(0xffffffffu, !skip);
       ++n_windows;
-      if (act == 0) { e0 += 32; continue; }
+      if (act == 0) { e0 += 32; if (lane == 0) s_cpos = e0; continue; }
       ++n_active;
       const int a = __ffs(act) - 1;
       e0 += a + 1;
       const int v = __shfl_sync(0xffffffffu, oslot, a), vis = __shfl_sync(0xffffffffu, ovis, a);
       const int r = __shfl_sync(0xffffffffu, ew.y, a);
-      // ---- the active seed: its 27 neighbour voxels (a visible voxel is its own neighbour 13)
-      int az, po, pi;
-      if (kSmem) { const uint32_t c = T.w[v] & kCoordMask; az = c & 511; po = (c >> 9) & 1023; pi = c >> 19; }
-      else { const int c = __ldcg(g_coord + v); az = c & 1023; po = (c >> 10) & 2047; pi = c >> 21; }
-      int nb = -1, kd = K_NONE, lb = -1;
-      if (lane < 27) {
-        const int z = pi - 1 + lane / 9, y = po - 1 + (lane / 3) % 3, x = az - 1 + lane % 3;
-        if (!(z < 0 || z > height) && !(y < 0 || y > polarNum)) {
-          int ax = x;
-          if (ax < 0) ax = width - 1;
-          if (ax > 300) ax = 300;
-          if (y < polarNum) nb = T.lookup(ax, y, z);  // polar index polarNum is legal for the guard but never occupied
-        }
-        if (nb >= 0) T.get(nb, kd, lb);
+      // ---- the active seed: its 27 neighbour voxels (a visible voxel is its own neighbour 13), looked up
+      //      ahead of time by a producer warp
+      const int ea = e0 - 1;
+      int nb;
+      if (use_rows) {
+        if (lane == 0) s_cpos = e0 - 1;
+        while (s_done[ea % kProducers + 1] <= ea) { }
+        __threadfence_block();
+        nb = lane < 27 ? s_rows[ea & (kRowRing - 1)][lane] : -1;
+      } else {
+        nb = neighbour(v);
       }
+      int kd = K_NONE, lb = -1;
+      if (nb >= 0) T.get(nb, kd, lb);
       const bool labelled = nb >= 0 && kd != K_NONE;
       const unsigned Lm = __ballot_sync(0xffffffffu, labelled);
 
@@ -516,6 +557,11 @@ __global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slo
           pt_label[r] = cur;
         }
       }
+      // Voxel states (global form) and label-forest entries beyond the shared-memory range live in global
+      // memory, written with plain stores by some lanes and read with ld.cg by others in the next event:
+      // __syncwarp alone did not order them on B200 (observed as wrong merges once the replaying warp got
+      // faster), a block-level fence does.
+      if (!kSmem || labelCount >= kUfCap) __threadfence_block();
       __syncwarp();
     }
     // publish the shared-memory part of the label forest for k_s1_finish
@@ -836,16 +882,19 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
       }
       S1_CUDA(cudaEventRecord(sp.ev[0], st));
       int lo = -1;
-      for (int c = 0; c < 4; ++c) {
+      const bool force_global = h->opt.s1_table == 1;  // tests: every task through the global-memory form
+      for (int c = 0; c < 4 && !force_global; ++c) {
         const int hi = kSlots[c] * 3 / 10;  // load factor <= 0.3
         cudaStream_t sc = sp.side[c];
         S1_CUDA(cudaStreamWaitEvent(sc, sp.ev[0], 0));
-        k_dcvc_replay<true><<<nt, kRpThreads, (size_t)kSlots[c] * 6, sc>>>(B, kSlots[c], lo, hi);
+        k_dcvc_replay<true><<<nt, kRpThreads, (size_t)kSlots[c] * 6, sc>>>(B, kSlots[c], lo, hi, h->opt.s1_rows);
         S1_CUDA(cudaEventRecord(sp.ev[1 + c], sc));
         lo = hi;
       }
-      k_dcvc_replay<false><<<nt, kRpThreads, 0, st>>>(B, 0, lo, 0x7fffffff);
-      for (int c = 0; c < 4; ++c) S1_CUDA(cudaStreamWaitEvent(st, sp.ev[1 + c], 0));
+      // the global form (tables too large for shared memory; rare) looks its rows up itself
+      k_dcvc_replay<false><<<nt, kRpThreads, 0, st>>>(B, 0, lo, 0x7fffffff, 0);
+      if (!force_global)
+        for (int c = 0; c < 4; ++c) S1_CUDA(cudaStreamWaitEvent(st, sp.ev[1 + c], 0));
     }
     trace("replay");
     k_s1_finish<<<nt, kS1Threads, 0, st>>>(B);

@@ -143,6 +143,8 @@ struct sgtd_options {
   int collect_group = 0;  // 0: all queries of the batch in one group
   int debug_novote = 0;   // 1: run the vote kernels without casting votes (kernel timing experiments)
   int s1_variant = 0;     // stage-1 class tables: 0 = gen_labels (get_json.cpp), 1 = local_map_creation (local_map.cpp)
+  int s1_table = 0;       // stage-1 replay table: 0 = shared memory when it fits, 1 = always the global-memory form (tests)
+  int s1_rows = 1;        // stage-1 replay: neighbour rows looked up ahead by producer warps (0: by the replaying warp)
   int s1_trace = 0;       // 1: stage 1 prints wall-clock checkpoints of its host driver on stderr
   int stats_unique = 0;   // 1: also count the distinct probed buckets / their entries (sgtd_vote_stats B, Eu)
   int join_impl = 1;      // 1 (default): k_vote_join, 16-byte float entries; experimental joins on 8-byte cell-relative

@@ -21,9 +21,18 @@ def compare(mgr, orc, pts, lab):
     return nodes, r
 
 
-@pytest.fixture(scope="module")
-def mgr():
-    return capi.STDescManager(device=0)
+# replay forms: shared-memory voxel table with neighbour rows produced ahead by helper warps (default), the
+# same with the replaying warp doing its own lookups, and the global-memory table every task falls back to
+# when its table does not fit shared memory (forced here so that ordinary scans exercise it)
+FORMS = {"smem+rows": dict(s1_rows=1, s1_table=0), "smem": dict(s1_rows=0, s1_table=0), "global": dict(s1_rows=1, s1_table=1)}
+
+
+@pytest.fixture(scope="module", params=list(FORMS))
+def mgr(request):
+    m = capi.STDescManager(device=0)
+    for k, v in FORMS[request.param].items():
+        m.set_option(k, v)
+    return m
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
@@ -34,9 +43,10 @@ def test_synthetic_scans_match_oracle(mgr, oracle_lib, seed):
 
 
 def test_random_clouds_stress_order_dependence(mgr, oracle_lib):
-    """Dense random blobs: many merges, head-only voxels, invisible top-pitch voxels."""
+    """Dense random blobs: many merges, head-only voxels, invisible top-pitch voxels.  Repeated: the replay
+    communicates between lanes and warps through memory, so a missing fence shows up as a flaky merge."""
     rng = np.random.default_rng(7)
-    for it in range(12):
+    for it in range(36):
         n = int(rng.integers(300, 6000))
         k = int(rng.integers(2, 12))
         centers = rng.uniform(-40, 40, (k, 3)) * np.array([1, 1, 0.1])
