@@ -229,6 +229,9 @@ int sgtd_set_option(sgtd_handle *h, const char *name, int32_t value) {
   else if (!strcmp(name, "collect_mode")) h->opt.collect_mode = (value >= 0 && value <= 2) ? value : 0;
   else if (!strcmp(name, "collect_group")) h->opt.collect_group = std::max(0, (int)value);
   else if (!strcmp(name, "debug_novote")) h->opt.debug_novote = value != 0;
+  else if (!strcmp(name, "join_parts")) h->opt.join_parts = (value >= 0 && value <= 4) ? (int)value : 0;
+  else if (!strcmp(name, "join_hint")) h->opt.join_hint = value != 0;
+  else if (!strcmp(name, "verify_impl")) h->opt.verify_impl = (int)value;
   else if (!strcmp(name, "join_impl")) {
     const int v = (value >= 0 && value <= 2) ? value : 1;
     if ((v == 1) != (h->opt.join_impl == 1)) h->dirty = true;  // 16-byte vs 8-byte entries: the index is rebuilt
@@ -238,6 +241,7 @@ int sgtd_set_option(sgtd_handle *h, const char *name, int32_t value) {
   else if (!strcmp(name, "s1_trace")) h->opt.s1_trace = value != 0;
   else if (!strcmp(name, "s1_variant")) h->opt.s1_variant = value == 1;
   else if (!strcmp(name, "s1_rows")) h->opt.s1_rows = value != 0;
+  else if (!strcmp(name, "s1_replay")) h->opt.s1_replay = value == 1;
   else if (!strcmp(name, "s1_table")) h->opt.s1_table = value == 1;
   else SGTD_FAIL(h, SGTD_E_INVALID, "unknown option");
   return SGTD_OK;
@@ -250,7 +254,7 @@ int sgtd_destroy(sgtd_handle *h) {
   if (h->nccl) nccl_api().CommDestroy((ncclComm_t)h->nccl);
   h->rec.release(); h->vert.release(); h->d_frame_off.release();
   h->v_s0.release(); h->v_s1.release(); h->v_s2.release(); h->v_frame.release(); h->v_pack.release(); h->v_pack8.release();
-  h->table.release(); h->f_key.release(); h->f_g.release(); h->f_side.release(); h->scratch.release(); h->stage_in.release(); h->uniq_bitmap.release();
+  h->table.release(); h->v_cut.release(); h->f_key.release(); h->f_g.release(); h->f_side.release(); h->scratch.release(); h->stage_in.release(); h->uniq_bitmap.release();
   if (h->s1pool && h->s1pool_free) h->s1pool_free(h->s1pool);
   if (h->gicp_pool && h->gicp_pool_free) h->gicp_pool_free(h->gicp_pool);
   for (auto *r : h->result_pool) destroy_result(r);

@@ -88,6 +88,7 @@ int finalize_db(sgtd_handle *h) {
   cudaStream_t st = h->stream;
   const int64_t N = (int64_t)h->rec.n;
   const int64_t F = h->frames_local();
+  h->v_cut_parts = 0;
   SGTD_CUDA(h, h->d_frame_off.reserve((size_t)F + 1, st, false));
   h->d_frame_off.n = (size_t)F + 1;
   SGTD_CUDA(h, cudaMemcpyAsync(h->d_frame_off.p, h->frame_off.data(), (size_t)(F + 1) * 8, cudaMemcpyHostToDevice, st));

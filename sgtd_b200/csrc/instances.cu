@@ -367,7 +367,7 @@ struct UnionFind2 {
 // nvox_lo < nvox <= nvox_hi selects the tasks of this launch (kSmem: table of `slots` entries in dynamic
 // shared memory); seeds that can create more labels than a 16-bit label holds go to the global form.
 template <bool kSmem>
-__global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slots, int nvox_lo, int nvox_hi, int use_rows) {
+__global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slots, int nvox_lo, int nvox_hi, int use_rows, int cc_max_ev) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ int s_parent[kUfCap];
   __shared__ uint32_t s_stamp[kUfCap];  // per root: (event number << 5 | 31 - lowest lane that saw it in that event)
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slo
   if (t.policy != P_DCVC) return;
   const TaskState ts = B.ts[blockIdx.x];
   const bool fits16 = ts.nvox + ts.ninvis < 65000;
-  if (kSmem) { if (!(ts.nvox > nvox_lo && ts.nvox <= nvox_hi && fits16)) return; }
+  if (kSmem) { if (!(ts.nvox > nvox_lo && ts.nvox <= nvox_hi && fits16) || ts.nevents <= cc_max_ev) return; }  // cc_max_ev: taken by k_dcvc_replay_cc
   else if (ts.nvox <= nvox_lo && fits16) return;
   const int tid = threadIdx.x, lane = tid & 31;
   const int height = ts.height, polarNum = ts.polarNum, width = ts.width;
@@ -587,6 +587,277 @@ __global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slo
     d[0] = c1 - c0; d[1] = c2 - c1; d[2] = c3 - c2; d[3] = clock64() - c3;
   }
 }
+
+// ---- K4b: component-parallel replay ---------------------------------------------------------------
+// Seed events only read and write the states of the seed's <= 27 neighbour voxels (and the labels living on
+// them), so events of different connected components of the voxel-neighbour graph commute; the only thing
+// they share is the counter that names new labels.  This form of the replay
+//   1. builds the shared-memory table and, per voxel, the index of its first event (as above);
+//   2. unions every voxel with its neighbour row (16-bit union-find over first-event indices, atomicCAS
+//      hooks the larger index under the smaller): components of the neighbour graph;
+//   3. hands the components to the CTA's 8 warps (greedy on the number of events, lightest warp first) and
+//      tags every event with its owner;
+//   4. lets all warps replay concurrently: a warp walks the event list with the same 32-wide windows as the
+//      sequential form, events of other warps count as skipped.  A new label is provisionally NAMED after the
+//      event that creates it (event index + 1); merges (parent[cur] = neigh) are structural, not by value;
+//   5. renames: the reference's label value is 1 + the number of label-creating events before it -- a prefix
+//      sum over the creation bitmap -- applied while the voxel states, the label forest and the labels of
+//      invisible seeds are written back.
+// Taken by tasks whose table fits the 2k / 8k / 16k-slot classes and that have at most kCcMaxEv events; the
+// rest go through the sequential forms.
+constexpr int kCcThreads = 256;
+constexpr int kCcWarps = kCcThreads / 32;
+constexpr int kCcMaxEv = 8192;
+constexpr int kCcRing = 256;
+
+__device__ __forceinline__ int uf16_find(volatile uint16_t *par, int x) {
+  while (true) { const int p = par[x]; if (p == x) return x; x = p; }
+}
+__device__ __forceinline__ void uf16_unite(uint16_t *par, int a, int b) {
+  while (true) {
+    a = uf16_find(par, a); b = uf16_find(par, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    if (atomicCAS(reinterpret_cast<unsigned short *>(par + a), (unsigned short)a, (unsigned short)b) == (unsigned short)a) return;
+  }
+}
+
+__global__ void __launch_bounds__(kCcThreads) k_dcvc_replay_cc(S1Buffers B, int slots, int nvox_lo, int nvox_hi) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ uint32_t s_new[kCcMaxEv / 32 + 1];  // bit e: event e created a label
+  __shared__ uint32_t s_pre[kCcMaxEv / 32 + 1];  // labels created before word w
+  __shared__ int s_tot[4];
+  const Task t = B.tasks[blockIdx.x];
+  if (t.policy != P_DCVC) return;
+  const TaskState ts = B.ts[blockIdx.x];
+  const int nev = ts.nevents;
+  if (!(ts.nvox > nvox_lo && ts.nvox <= nvox_hi && nev <= kCcMaxEv)) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int height = ts.height, polarNum = ts.polarNum, width = ts.width;
+  VoxTable<true> T{};
+  T.w = reinterpret_cast<uint32_t *>(s_dyn); T.lab = reinterpret_cast<uint16_t *>(s_dyn + (size_t)slots * 4); T.mask = (uint32_t)slots - 1;
+  uint16_t *s_a = reinterpret_cast<uint16_t *>(s_dyn + (size_t)slots * 6);           // union-find of the components, then of the labels
+  uint16_t *s_b = s_a + (kCcMaxEv + 2);                                              // root of each event, then the warps' event rings
+  int2 *s_ring = reinterpret_cast<int2 *>(s_dyn + (size_t)slots * 6 + 2 * (size_t)(kCcMaxEv + 2) * 2);
+  int4 *events = B.events + t.idx_off;
+  int2 *evc = B.evc + t.idx_off;
+  int *pt_label = B.pt_label + t.idx_off;
+  const long long c0 = clock64();
+  // ---- 1. table, first event of each voxel, replay form of the events
+  for (int i = tid; i < slots; i += kCcThreads) { T.w[i] = kVEmpty; T.lab[i] = 0; }
+  for (int i = tid; i <= kCcMaxEv / 32; i += kCcThreads) s_new[i] = 0;
+  if (tid < 4) s_tot[tid] = 0;
+  __syncthreads();
+#pragma unroll 4
+  for (int e = tid; e < nev; e += kCcThreads) {
+    const int4 ev = events[e];
+    s_a[e] = (uint16_t)e;
+    if (!(ev.w & 1)) continue;
+    const int c = ev.z;
+    const uint32_t key = coord27(c & 1023, (c >> 10) & 2047, c >> 21);
+    uint32_t pos = hash_u32(key) & T.mask;
+    while (atomicCAS(&T.w[pos], kVEmpty, key) != kVEmpty) pos = (pos + 1) & T.mask;
+    T.lab[pos] = (uint16_t)e;
+  }
+  __syncthreads();
+  const long long c1 = clock64();
+  auto neighbour = [&](int slot) -> int {
+    const uint32_t c = T.w[slot] & kCoordMask;
+    const int az = c & 511, po = (c >> 9) & 1023, pi = c >> 19;
+    int nb = -1;
+    if (lane < 27) {
+      const int z = pi - 1 + lane / 9, y = po - 1 + (lane / 3) % 3, x = az - 1 + lane % 3;
+      if (!(z < 0 || z > height) && !(y < 0 || y > polarNum)) {
+        int ax = x;
+        if (ax < 0) ax = width - 1;
+        if (ax > 300) ax = 300;
+        if (y < polarNum) nb = T.lookup(ax, y, z);
+      }
+    }
+    return nb;
+  };
+  // ---- 2. own slot of every event; components: every voxel united with its neighbour row
+  for (int e0 = wid * 32; e0 < nev; e0 += kCcThreads) {
+    const int e = e0 + lane;
+    int4 ev = make_int4(0, 0, 0, 0);
+    int slot = 0;
+    if (e < nev) {
+      ev = events[e];
+      const int c = ev.z;
+      slot = T.lookup(c & 1023, (c >> 10) & 2047, c >> 21);
+      const int vis = (c >> 21) <= height;
+      evc[e] = make_int2(slot | (ev.w << 28) | (vis << 30), ev.x);
+    }
+    unsigned firsts = __ballot_sync(0xffffffffu, e < nev && (ev.w & 1));
+    while (firsts) {
+      const int j = __ffs(firsts) - 1;
+      firsts &= firsts - 1;
+      const int nb = neighbour(__shfl_sync(0xffffffffu, slot, j));
+      if (nb >= 0) uf16_unite(s_a, e0 + j, (int)T.lab[nb]);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- 3. root and weight of every component, owners
+  for (int e = tid; e < nev; e += kCcThreads) s_b[e] = (uint16_t)uf16_find(s_a, (int)T.lab[evc[e].x & 0xFFFF]);
+  __syncthreads();
+  uint32_t *s_a32 = reinterpret_cast<uint32_t *>(s_a);
+  for (int i = tid; i < (kCcMaxEv + 2) / 2; i += kCcThreads) s_a32[i] = 0;
+  __syncthreads();
+  for (int e = tid; e < nev; e += kCcThreads) { const uint32_t r = s_b[e]; atomicAdd(&s_a32[r >> 1], 1u << (16 * (r & 1u))); }  // <= 8192 per half
+  __syncthreads();
+  if (wid == 0) {
+    int load[kCcWarps];
+#pragma unroll
+    for (int w = 0; w < kCcWarps; ++w) load[w] = 0;
+    for (int e0 = 0; e0 < nev; e0 += 32) {
+      const int e = e0 + lane;
+      unsigned roots = __ballot_sync(0xffffffffu, e < nev && s_b[e] == (uint16_t)e);
+      while (roots) {
+        const int j = __ffs(roots) - 1;
+        roots &= roots - 1;
+        const int wgt = s_a[e0 + j];
+        int best = 0;
+#pragma unroll
+        for (int w = 1; w < kCcWarps; ++w) if (load[w] < load[best]) best = w;
+#pragma unroll
+        for (int w = 0; w < kCcWarps; ++w) if (w == best) load[w] += wgt;
+        if (lane == 0) s_a[e0 + j] = (uint16_t)best;  // the root's entry now holds the owner
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < nev; e += kCcThreads) { int2 v = evc[e]; v.x |= (int)s_a[s_b[e]] << 16; evc[e] = v; }
+  __threadfence_block();
+  __syncthreads();
+  const long long c2 = clock64();
+  // ---- 4. replay: every warp walks the whole event list and takes the seeds of its own components
+  {
+    uint16_t *lpar = s_a;  // label forest, indexed by the provisional label (creating event + 1)
+    int2 *ring = s_ring + wid * kCcRing;
+    auto lfind = [&](int x) -> int {
+      while (true) {
+        const int p = lpar[x];
+        if (p == x) return x;
+        const int g = lpar[p];
+        if (g != p) lpar[x] = (uint16_t)g;
+        x = g;
+      }
+    };
+    int n_active = 0, n_windows = 0, n_labels = 0;
+    int loaded = 0, pre_base = 0;
+    int2 pre[4];
+    auto prefetch = [&](int base) {
+      pre_base = base;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const int i = base + 32 * j + lane; pre[j] = i < nev ? evc[i] : make_int2(0, 0); }
+    };
+    auto commit = [&]() {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ring[(pre_base + 32 * j + lane) & (kCcRing - 1)] = pre[j];
+      loaded = min(nev, pre_base + 128);
+      __syncwarp();
+    };
+    prefetch(0); commit(); prefetch(128);
+    int e0 = 0;
+    while (e0 < nev) {
+      if (e0 + 32 > loaded && loaded < nev) { commit(); prefetch(loaded); }
+      const int ei = e0 + lane;
+      const bool valid = ei < nev;
+      const int2 ew = valid ? ring[ei & (kCcRing - 1)] : make_int2(0, 0);
+      const int oslot = ew.x & 0xFFFF, owner = (ew.x >> 16) & 7, which = (ew.x >> 28) & 3, ovis = (ew.x >> 30) & 1;
+      bool skip = !valid || owner != wid;
+      if (!skip && ovis) {
+        const int kd = T.kind(oslot);
+        skip = kd == K_ALL || (kd == K_NONE && !(which & 1)) || (kd == K_HEAD && !(which & 2));
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, !skip);
+      ++n_windows;
+      if (act == 0) { e0 += 32; continue; }
+      ++n_active;
+      const int a = __ffs(act) - 1;
+      e0 += a + 1;
+      const int v = __shfl_sync(0xffffffffu, oslot, a), vis = __shfl_sync(0xffffffffu, ovis, a);
+      const int r = __shfl_sync(0xffffffffu, ew.y, a);
+      const int ea = e0 - 1;
+      const int nb = neighbour(v);
+      int kd = K_NONE, lb = -1;
+      if (nb >= 0) T.get(nb, kd, lb);
+      const bool labelled = nb >= 0 && kd != K_NONE;
+      const unsigned Lm = __ballot_sync(0xffffffffu, labelled);
+      int root = -1;
+      if (labelled) root = lfind(lb);
+      __syncwarp();
+      bool is_first = false;
+      if (labelled) { const unsigned grp = __match_any_sync(Lm, root); is_first = lane == __ffs(grp) - 1; }
+      const unsigned Fm = __ballot_sync(0xffffffffu, is_first);
+      if (Fm == 0) {  // no labelled neighbour: new label for the seed and every neighbour (:340-346)
+        const int L = ea + 1;
+        ++n_labels;
+        if (lane == 0) { lpar[L] = (uint16_t)L; atomicOr(&s_new[ea >> 5], 1u << (ea & 31)); if (!vis) pt_label[r] = L; }
+        if (nb >= 0) T.set(nb, K_ALL, L);
+      } else {
+        const unsigned after = Fm & ~((2u << lane) - 1u);
+        const int nroot = __shfl_sync(0xffffffffu, root, after ? __ffs(after) - 1 : lane);
+        if (is_first && after) lpar[root] = (uint16_t)nroot;
+        const int cur = __shfl_sync(0xffffffffu, root, 31 - __clz(Fm));
+        const unsigned before = Fm & ((1u << lane) - 1u);
+        const int cprev = __shfl_sync(0xffffffffu, root, before ? 31 - __clz(before) : lane);
+        const bool takes = nb >= 0 && kd == K_NONE && before;
+        if (takes) T.set(nb, K_ALL, cprev);
+        if (labelled && kd == K_HEAD) T.set_kind(nb, K_ALL);
+        if (vis) {
+          const unsigned self = __ballot_sync(0xffffffffu, nb == v && (takes || labelled));
+          if (!self && lane == 0) T.set(v, K_HEAD, cur);
+        } else if (lane == 0) {
+          pt_label[r] = cur;
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) { atomicAdd(&s_tot[0], n_active); atomicAdd(&s_tot[1], n_windows); atomicAdd(&s_tot[2], n_labels); }
+  }
+  __threadfence_block();
+  __syncthreads();
+  const long long c3 = clock64();
+  // ---- 5. the reference's label values, write-back
+  if (wid == 0) {
+    int run = 0;
+    for (int w0 = 0; w0 <= kCcMaxEv / 32; w0 += 32) {
+      const int w = w0 + lane;
+      const int cnt = (w <= kCcMaxEv / 32) ? __popc(s_new[w]) : 0;
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+      if (w <= kCcMaxEv / 32) s_pre[w] = (uint32_t)(run + inc - cnt);
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+  auto final_label = [&](int L) -> int {  // provisional (creating event + 1) -> 1 + number of creating events before it
+    const int e = L - 1;
+    return (int)s_pre[e >> 5] + __popc(s_new[e >> 5] & ((1u << (e & 31)) - 1u)) + 1;
+  };
+  int *g_kind = B.t_kind + t.tab_off, *g_label = B.t_label + t.tab_off, *g_parent = B.parent + t.lab_off;
+#pragma unroll 2
+  for (int e = tid; e < nev; e += kCcThreads) {
+    const int4 ev = events[e];
+    const int2 ec = evc[e];
+    if (ev.w & 1) {
+      int kd, lb;
+      T.get(ec.x & 0xFFFF, kd, lb);
+      g_kind[ev.y] = kd; g_label[ev.y] = kd == K_NONE ? -1 : final_label(lb);
+    }
+    if (!((ec.x >> 30) & 1)) pt_label[ec.y] = final_label(pt_label[ec.y]);
+    if ((s_new[e >> 5] >> (e & 31)) & 1u) g_parent[final_label(e + 1)] = final_label((int)s_a[e + 1]);
+  }
+  if (tid == 0) {
+    TaskState &o = B.ts[blockIdx.x];
+    o.labelCount = s_tot[2]; o.dbg_active = s_tot[0]; o.dbg_windows = s_tot[1];
+    o.dbg_cyc[0] = c1 - c0; o.dbg_cyc[1] = c2 - c1; o.dbg_cyc[2] = c3 - c2; o.dbg_cyc[3] = clock64() - c3;
+  }
+}
+constexpr size_t kCcExtraSmem = 2 * (size_t)(kCcMaxEv + 2) * 2 + (size_t)kCcWarps * kCcRing * sizeof(int2);
 
 // ---- K5: final label per point, per-label size and first point, compact label list -------
 __global__ void __launch_bounds__(kS1Threads) k_s1_finish(S1Buffers B) {
@@ -883,16 +1154,21 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
       S1_CUDA(cudaEventRecord(sp.ev[0], st));
       int lo = -1;
       const bool force_global = h->opt.s1_table == 1;  // tests: every task through the global-memory form
+      // default: the component-parallel form for the three smaller classes (option s1_replay = 1: sequential forms only)
+      const bool use_cc = h->opt.s1_replay == 0;
+      if (use_cc) S1_CUDA(cudaFuncSetAttribute(k_dcvc_replay_cc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSlots[2] * 6 + kCcExtraSmem)));
       for (int c = 0; c < 4 && !force_global; ++c) {
         const int hi = kSlots[c] * 3 / 10;  // load factor <= 0.3
         cudaStream_t sc = sp.side[c];
         S1_CUDA(cudaStreamWaitEvent(sc, sp.ev[0], 0));
-        k_dcvc_replay<true><<<nt, kRpThreads, (size_t)kSlots[c] * 6, sc>>>(B, kSlots[c], lo, hi, h->opt.s1_rows);
+        const bool cc = use_cc && c < 3;
+        if (cc) k_dcvc_replay_cc<<<nt, kCcThreads, (size_t)kSlots[c] * 6 + kCcExtraSmem, sc>>>(B, kSlots[c], lo, hi);
+        k_dcvc_replay<true><<<nt, kRpThreads, (size_t)kSlots[c] * 6, sc>>>(B, kSlots[c], lo, hi, h->opt.s1_rows, cc ? kCcMaxEv : -1);
         S1_CUDA(cudaEventRecord(sp.ev[1 + c], sc));
         lo = hi;
       }
       // the global form (tables too large for shared memory; rare) looks its rows up itself
-      k_dcvc_replay<false><<<nt, kRpThreads, 0, st>>>(B, 0, lo, 0x7fffffff, 0);
+      k_dcvc_replay<false><<<nt, kRpThreads, 0, st>>>(B, 0, lo, 0x7fffffff, 0, -1);
       if (!force_global)
         for (int c = 0; c < 4; ++c) S1_CUDA(cudaStreamWaitEvent(st, sp.ev[1 + c], 0));
     }

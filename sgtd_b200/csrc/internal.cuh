@@ -145,8 +145,12 @@ struct sgtd_options {
   int s1_variant = 0;     // stage-1 class tables: 0 = gen_labels (get_json.cpp), 1 = local_map_creation (local_map.cpp)
   int s1_table = 0;       // stage-1 replay table: 0 = shared memory when it fits, 1 = always the global-memory form (tests)
   int s1_rows = 1;        // stage-1 replay: neighbour rows looked up ahead by producer warps (0: by the replaying warp)
+  int s1_replay = 0;      // stage-1 replay: 0 = component-parallel form where it applies, 1 = sequential forms only
   int s1_trace = 0;       // 1: stage 1 prints wall-clock checkpoints of its host driver on stderr
   int stats_unique = 0;   // 1: also count the distinct probed buckets / their entries (sgtd_vote_stats B, Eu)
+  int join_parts = 0;     // keyframe-range parts per query group of k_vote_join (0/1: none; 2..4)
+  int verify_impl = 0;    // experiments on k_verify (0: default)
+  int join_hint = 0;      // 1: vote REDs carry an L2 evict-last policy
   int join_impl = 1;      // 1 (default): k_vote_join, 16-byte float entries; experimental joins on 8-byte cell-relative
                           // entries (index rebuilt on request): 0 = k_vote_join8 (per-lane loads), 2 = k_vote_run
                           // (bulk-async staged tiles).  Measured on the bench workload: 9.0 / 11.4 / 12.6 ms.
@@ -178,6 +182,8 @@ struct sgtd_handle {
   sgtd::DevBuf<float4> v_pack;     // {float s0, s1, s2, frame bits}: what the round-1 k_vote_join streams (16 B/entry; on request)
   sgtd::DevBuf<uint64_t> v_pack8;  // cell-relative 13-bit sides + 25-bit frame: what the join streams (8 B/entry)
   sgtd::DevBuf<sgtd::Bucket> table;
+  sgtd::DevBuf<uint32_t> v_cut;    // per table slot: starts of the keyframe-range parts inside the bucket (join_parts > 1)
+  int v_cut_parts = 0;             // parts v_cut was built for (0: stale)
   uint64_t table_mask = 0;
   int64_t n_buckets = 0;
   // per-keyframe key-sorted view (for match-list materialisation)

@@ -97,7 +97,7 @@ static_assert(sizeof(JoinDesc) == 48, "JoinDesc");
 
 __global__ void k_qaux(const DescRec *q, const int64_t *q_off, int nq, int64_t nd, double rough, QAux *aux,
                        uint64_t *skey, uint32_t *sidx, JoinDesc *jd, double band, uint32_t frame_lo,
-                       uint32_t *votes, int64_t F) {
+                       uint32_t *votes, int64_t F, uint32_t *qprobes) {
   const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= nd) return;
   const DescRec r = q[d];
@@ -110,6 +110,21 @@ __global__ void k_qaux(const DescRec *q, const int64_t *q_off, int nq, int64_t n
   while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (q_off[mid] <= d) lo = mid; else hi = mid - 1; }
   a.qi = (uint32_t)lo;
   aux[d] = a;
+  {  // probes of each query (sizes its probe multimap, k_query_index): one atomic per run of equal queries in the warp
+    const unsigned act = __activemask();
+    const int ln = threadIdx.x & 31;
+    const uint32_t up = __shfl_up_sync(act, (uint32_t)lo, 1);
+    const bool head = ln == 0 || !((act >> (ln - 1)) & 1u) || up != (uint32_t)lo;
+    const unsigned heads = __ballot_sync(act, head);
+    // inclusive prefix of the probe counts, then run sum = prefix at the run's last lane - prefix before its head
+    uint32_t inc = (uint32_t)__popc(m);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(act, inc, o); if (ln >= o && ((act >> (ln - o)) & 1u)) inc += v; }
+    const unsigned later = heads & ~((2u << ln) - 1u);  // run heads after this lane
+    const int last = later ? __ffs(later) - 2 : 31 - __clz(act);
+    const uint32_t end = __shfl_sync(act, inc, last);
+    if (head) atomicAdd(&qprobes[lo], end - (inc - (uint32_t)__popc(m)));
+  }
   if (jd) {
     JoinDesc j;
     j.s0a = j.s0b = (float)r.s[0]; j.s1a = j.s1b = (float)r.s[1]; j.s2a = j.s2b = (float)r.s[2];
@@ -337,7 +352,51 @@ struct JoinParams {
   uint32_t *votes;
   unsigned long long *seg_counter, *counters;
   uint32_t slot_mask;
+  // pass plan (k_join_plan): the sorted pairs are walked query-group by query-group and, inside a group,
+  // keyframe-range part by part; a pass only touches the vote rows of (group, part)
+  const unsigned long long *plan;  // [0, ngroups]: first pair of each group; [kPlanMax + 1 ...]: first ticket of each group
+  const uint32_t *cut;             // parts > 1: per table slot, parts - 1 positions inside the bucket (first entry of part j + 1)
+  int ngroups, parts;
+  uint32_t group_shift;
 };
+constexpr int kPlanMax = 32;  // query groups at most
+
+// One warp: where each query group starts in the sorted pair list (the group is the high part of the sort
+// key) and the ticket range of its passes (parts x segments of kJoinSeg pairs).
+__global__ void k_join_plan(const uint32_t *pkey, unsigned long long npairs, uint32_t group_shift, int ngroups, int parts,
+                            unsigned long long *plan) {
+  const int g = threadIdx.x;
+  if (g <= ngroups) {
+    unsigned long long lo = 0, hi = npairs;
+    while (lo < hi) {
+      const unsigned long long mid = (lo + hi) >> 1;
+      if ((pkey[mid] >> group_shift) < (uint32_t)g) lo = mid + 1; else hi = mid;
+    }
+    plan[g] = (g == ngroups) ? npairs : lo;
+  }
+  __syncwarp();
+  if (g == 0) {
+    unsigned long long t = 0;
+    for (int i = 0; i <= ngroups; ++i) {
+      plan[kPlanMax + 1 + i] = t;
+      if (i < ngroups) t += (unsigned long long)parts * ((plan[i + 1] - plan[i] + 31) / 32);
+    }
+  }
+}
+
+// Per table slot: where the keyframe-range parts of its bucket start (entries of a bucket are in keyframe
+// order).  cut[slot * (parts - 1) + j] = first entry (relative to the bucket) whose local frame is >= (j + 1) * fpart.
+__global__ void k_bucket_cuts(const Bucket *table, uint64_t nslots, const uint32_t *fr, int parts, uint32_t fpart, uint32_t *cut) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  const Bucket b = table[s];
+  for (int j = 0; j < parts - 1; ++j) {
+    uint32_t lo = 0, hi = (b.key == SGTD_EMPTY_KEY) ? 0 : b.cnt;
+    const uint32_t bound = (uint32_t)(j + 1) * fpart;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (fr[(size_t)b.off + mid] < bound) lo = mid + 1; else hi = mid; }
+    cut[s * (uint64_t)(parts - 1) + j] = lo;
+  }
+}
 
 // FP32 pre-filter of the rough distance test.  DB sides are also kept as float (16-byte packed entry
 // {s0, s1, s2, frame}); s = ||q - e||^2 - thr^2 is first formed in float (packed FP32, two entries per
@@ -349,17 +408,19 @@ struct JoinParams {
 // evaluated.  Halves the bytes per entry and moves the test to the FP32 pipe.
 // Exact (reference) evaluation of the entries a lane found inside the FP32 decision band.
 template <bool kDoVote>
-__device__ __noinline__ uint32_t join_exact(const JoinParams &P, const double *qs, uint32_t *row, uint32_t o, uint32_t n,
-                                            uint32_t e_first, uint32_t amb) {
+// (takes the pointers it needs by value: a reference to the kernel's parameter struct forces a stack copy of it)
+__device__ __noinline__ uint32_t join_exact(const double *s0, const double *s1, const double *s2, const uint32_t *frp,
+                                            const double *qs, uint32_t *row, uint32_t o, uint32_t n, uint32_t e_first,
+                                            uint32_t amb) {
   uint32_t hits = 0;
   while (amb) {
     const int u = __ffs(amb) - 1;
     amb &= amb - 1;
     const uint32_t e = e_first + 32 * u;
     const size_t idx = (size_t)o + (e < n ? e : n - 1);
-    const double d2 = sqn3(__dsub_rn(qs[0], P.s0[idx]), __dsub_rn(qs[1], P.s1[idx]), __dsub_rn(qs[2], P.s2[idx]));
+    const double d2 = sqn3(__dsub_rn(qs[0], s0[idx]), __dsub_rn(qs[1], s1[idx]), __dsub_rn(qs[2], s2[idx]));
     if (d2 < qs[3]) {
-      if (kDoVote) atomicAdd(row + P.fr[idx], 1u);
+      if (kDoVote) atomicAdd(row + frp[idx], 1u);
       ++hits;
     }
   }
@@ -379,23 +440,44 @@ __device__ __forceinline__ void red_inc_if(uint32_t *addr, bool hit) {
                : "memory");
 }
 
+// the same with an L2 evict-last hint: the vote rows of the running pass are what has to stay in L2 while
+// the bucket tiles stream past them
+__device__ __forceinline__ void red_inc_if_keep(uint32_t *addr, bool hit, uint64_t policy) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0;\n @p red.global.add.L2::cache_hint.u32 [%0], 1, %2;\n}" ::"l"(addr),
+               "r"((uint32_t)hit), "l"(policy)
+               : "memory");
+}
+
 static_assert(kVoteUnroll == 4, "k_vote_join pairs the entries of a trip as (0,1) and (2,3)");
-template <bool kDoVote>
+// kHint: REDs carry an L2 evict-last policy
+template <bool kDoVote, bool kHint>
 __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
   __shared__ double sh_s[kVoteThreads / 32][kJoinSeg][4];  // s0, s1, s2, thr2 of each probe of the segment (exact path)
   __shared__ float4 sh_f[kVoteThreads / 32][kJoinSeg];     // float s0, s1, s2, -thr2
   __shared__ uint4 sh_g[kVoteThreads / 32][kJoinSeg];      // band half-width w (float bits), query frame id, vote row pointer
+  __shared__ unsigned long long sh_plan[2 * (kPlanMax + 1)];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned long long nseg = (P.npairs + kJoinSeg - 1) / kJoinSeg;
+  for (int i = threadIdx.x; i < 2 * (kPlanMax + 1); i += kVoteThreads) sh_plan[i] = P.plan[i];
+  __syncthreads();
+  const unsigned long long *g_first = sh_plan, *g_ticket = sh_plan + kPlanMax + 1;
+  const unsigned long long ntickets = g_ticket[P.ngroups];
   const f32x2 negzero2 = pack2(-0.f, -0.f);
+  uint64_t policy = 0;
+  if (kHint) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
   uint32_t cM = 0;  // matches seen by this thread (only counted here when no votes are cast; else k_topk sums the rows)
   while (true) {
-    unsigned long long seg = 0;
-    if (lane == 0) seg = atomicAdd(P.seg_counter, 1ull);
-    seg = __shfl_sync(0xffffffffu, seg, 0);
-    if (seg >= nseg) break;
-    const unsigned long long p0 = seg * kJoinSeg;
-    const int np = (int)min((unsigned long long)kJoinSeg, P.npairs - p0);
+    unsigned long long tk = 0;
+    if (lane == 0) tk = atomicAdd(P.seg_counter, 1ull);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= ntickets) break;
+    // ticket -> (query group, keyframe part, segment of the group)
+    const int grp = __popc(__ballot_sync(0xffffffffu, lane < P.ngroups && g_ticket[lane + 1] <= tk));
+    const unsigned long long gp0 = g_first[grp], gp1 = g_first[grp + 1];
+    const uint32_t gseg = (uint32_t)((gp1 - gp0 + kJoinSeg - 1) / kJoinSeg);  // < 2^32 pairs per batch
+    const uint32_t rel = (uint32_t)(tk - g_ticket[grp]);
+    const int part = (P.parts > 1) ? (int)(rel / gseg) : 0;
+    const unsigned long long p0 = gp0 + (unsigned long long)(rel - (uint32_t)part * gseg) * kJoinSeg;
+    const int np = (int)min((unsigned long long)kJoinSeg, gp1 - p0);
     uint32_t slot = 0xFFFFFFFFu;
     __syncwarp();
     if (lane < np) {
@@ -416,8 +498,14 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
       const uint32_t cur = __shfl_sync(0xffffffffu, slot, i);
       const int run = __popc(__ballot_sync(0xffffffffu, slot == cur));  // sorted: equal slots are contiguous from i
       const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.table[cur & P.slot_mask]));
-      const uint32_t o = raw.z, n = raw.w;
-      for (uint32_t e0 = 0; e0 < n; e0 += 32 * kVoteUnroll) {
+      const uint32_t o = raw.z;
+      uint32_t n = raw.w, e_lo = 0;  // this pass streams entries [e_lo, n) of the bucket: its keyframe part
+      if (P.parts > 1) {
+        const uint32_t *c = P.cut + (size_t)(cur & P.slot_mask) * (uint32_t)(P.parts - 1);
+        if (part > 0) e_lo = __ldg(c + part - 1);
+        if (part < P.parts - 1) n = __ldg(c + part);
+      }
+      for (uint32_t e0 = e_lo; e0 < n; e0 += 32 * kVoteUnroll) {
         float4 v[kVoteUnroll];
 #pragma unroll
         for (int u = 0; u < kVoteUnroll; ++u) {
@@ -455,7 +543,7 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
 #pragma unroll
           for (int u = 0; u < kVoteUnroll; ++u) {
             const bool hit = (fr[u] != g.y) && sd[u] < -wb;  // certainly a match
-            if (kDoVote) red_inc_if(row + fr[u], hit);
+            if (kDoVote) { if (kHint) red_inc_if_keep(row + fr[u], hit, policy); else red_inc_if(row + fr[u], hit); }
             else cM += hit;
           }
           const float nearest = fminf(fminf(fabsf(sd[0]), fabsf(sd[1])), fminf(fabsf(sd[2]), fabsf(sd[3])));
@@ -464,7 +552,7 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
 #pragma unroll
             for (int u = 0; u < kVoteUnroll; ++u)
               if ((fr[u] != g.y) && fabsf(sd[u]) <= wb) amb |= 1u << u;
-            if (amb) cM += join_exact<kDoVote>(P, sh_s[wid][p], row, o, n, e0 + lane, amb);
+            if (amb) cM += join_exact<kDoVote>(P.s0, P.s1, P.s2, P.fr, sh_s[wid][p], row, o, n, e0 + lane, amb);
           }
         }
       }
@@ -1030,10 +1118,18 @@ constexpr int kSortCap = 4096;        // matches of a candidate
 constexpr int kInvMaxDesc = 8192;     // descriptors of its query (13 bits of the record)
 constexpr int kInvMaxEntries = 4096;  // entries of its keyframe (12 bits of the record)
 constexpr int kInvBinSort = 32;       // larger per-descriptor groups: the whole list is sorted instead
-constexpr unsigned long long kQtEmpty = 0xFFFFFFFFFFFFFFFFull;
-// A slot is (tag << 32) | (descriptor << 5 | ordinal): tag = high half of the key's hash (the low bits
-// give the position), so one 64-bit CAS inserts a probe and one 8-byte read tests it.  A tag hit is
-// confirmed against the key recomputed from the query descriptor, so the result stays exact.
+constexpr uint32_t kQtEmpty = 0xFFFFFFFFu;
+// A slot is tag:14 | descriptor:13 | ordinal:5 -- tag = the top bits of the key's hash (the low bits give the
+// position), so one 32-bit CAS inserts a probe and one 4-byte read tests it (ordinal 31 never occurs: the
+// all-ones word is the empty slot).  A tag hit is confirmed against the key recomputed from the query
+// descriptor, so the result stays exact.  The table of a query has qt_size(probes of the query) slots
+// (load <= 0.25: chains of a multimap lengthen quickly above that) inside a stride sized for the worst case (27 probes per descriptor of the largest query).
+__host__ __device__ inline uint32_t qt_size(uint32_t probes, uint32_t stride) {
+  uint32_t ts = 64;
+  while (ts < 4u * probes && ts < stride) ts <<= 1;
+  return ts;
+}
+__device__ __forceinline__ uint32_t qt_tag(unsigned long long hsh) { return (uint32_t)(hsh >> 50); }
 __device__ __forceinline__ bool inv_eligible(int nmatch, int64_t ndq, int nf) {
   return nmatch <= kSortCap && ndq <= kInvMaxDesc && nf <= kInvMaxEntries;
 }
@@ -1219,8 +1315,8 @@ constexpr int kIndexThreads = 1024;
 // One CTA per query: clears the query's table (it then sits in L2: 148 resident tables of ~0.6 MB) and
 // inserts every probe with one CAS.
 __global__ void __launch_bounds__(kIndexThreads) k_query_index(const DescRec *q, const QAux *aux, const int64_t *q_off,
-                                                               int q_base, unsigned long long *qt, uint32_t ts,
-                                                               const sgtd_candidate *cands, int k) {
+                                                               int q_base, uint32_t *qt, uint32_t stride,
+                                                               const uint32_t *qprobes, const sgtd_candidate *cands, int k) {
   const int qi = q_base + blockIdx.x;  // tables are indexed by the query's position inside its group
   // a query none of whose candidates is materialised on this rank (sharded database: the candidates of a
   // query cluster in one or two keyframe-range shards) needs no table
@@ -1236,12 +1332,13 @@ __global__ void __launch_bounds__(kIndexThreads) k_query_index(const DescRec *q,
     if (!s_any) return;
   }
   const int64_t q0 = q_off[qi], q1 = q_off[qi + 1];
-  unsigned long long *tk = qt + (size_t)blockIdx.x * ts;
-  const uint32_t mask = ts - 1;
+  if (q1 - q0 > kInvMaxDesc) return;  // its candidates are not eligible for the inverted form
+  uint32_t *tk = qt + (size_t)blockIdx.x * stride;
+  const uint32_t ts = qt_size(qprobes[qi], stride), mask = ts - 1;
   {
-    const ulonglong2 e2 = make_ulonglong2(kQtEmpty, kQtEmpty);
-    ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(tk);
-    for (uint32_t i = threadIdx.x; i < ts / 2; i += kIndexThreads) t2[i] = e2;
+    const uint4 e4 = make_uint4(kQtEmpty, kQtEmpty, kQtEmpty, kQtEmpty);
+    uint4 *t4 = reinterpret_cast<uint4 *>(tk);
+    for (uint32_t i = threadIdx.x; i < ts / 4; i += kIndexThreads) t4[i] = e4;
   }
   __syncthreads();
   for (int64_t d = q0 + threadIdx.x; d < q1; d += kIndexThreads) {
@@ -1252,7 +1349,7 @@ __global__ void __launch_bounds__(kIndexThreads) k_query_index(const DescRec *q,
       const int ord = __ffs(m) - 1;
       m &= m - 1;
       const unsigned long long hsh = mix64(probe_cell_key(r, ord));
-      const unsigned long long val = (hsh & 0xFFFFFFFF00000000ull) | (unsigned long long)((il << 5) | (uint32_t)ord);
+      const uint32_t val = (qt_tag(hsh) << 18) | (il << 5) | (uint32_t)ord;
       uint32_t pos = (uint32_t)hsh & mask;
       while (atomicCAS(&tk[pos], kQtEmpty, val) != kQtEmpty) pos = (pos + 1) & mask;  // one slot per probe
     }
@@ -1263,7 +1360,8 @@ struct CollectInvParams {
   const sgtd_candidate *cands;
   int k;
   const DescRec *q; const QAux *aux; const int64_t *q_off;
-  const unsigned long long *qt; uint32_t ts;
+  const uint32_t *qt; uint32_t stride;
+  const uint32_t *qprobes;
   int q_base;  // first query of the group the tables were built for
   const int64_t *frame_off; const uint64_t *f_key; const uint32_t *f_g; const double *f_side;
   int64_t frame_lo;
@@ -1279,7 +1377,7 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect_inv(CollectInvParam
   uint32_t *s_out = s_rec + kSortCap;
   uint32_t *s_bin32 = s_out + kSortCap;
   uint16_t *s_bin16 = reinterpret_cast<uint16_t *>(s_bin32);
-  __shared__ uint32_t s_n, s_big, s_wsum[kCollectThreads / 32];
+  __shared__ uint32_t s_n, s_big, s_qn, s_wsum[kCollectThreads / 32];
   const size_t cslot = (size_t)P.q_base * P.k + blockIdx.x;
   const sgtd_candidate c = P.cands[cslot];
   if (c.match_off < 0 || c.nmatch <= 0) return;
@@ -1291,16 +1389,34 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect_inv(CollectInvParam
   const int64_t q0 = P.q_off[q];
   const int ndq = (int)(P.q_off[q + 1] - q0);
   if (!inv_eligible(c.nmatch, ndq, nf)) return;
-  const unsigned long long *tk = P.qt + (size_t)(q - P.q_base) * P.ts;
-  const uint32_t mask = P.ts - 1;
-  if (tid == 0) { s_n = 0; s_big = 0; }
+  const uint32_t *tk = P.qt + (size_t)(q - P.q_base) * P.stride;
+  const uint32_t mask = qt_size(P.qprobes[q], P.stride) - 1;
+  if (tid == 0) { s_n = 0; s_big = 0; s_qn = 0; }
   for (int i = tid; i < (ndq + 1) / 2; i += kCollectThreads) s_bin32[i] = 0;
   __syncthreads();
   // ---- lookups: record = descriptor (13 bits) | ordinal (5) | position in the key-sorted view (12);
-  // equal keys keep in-frame order in the view, so position order == the reference's bucket order j
+  // equal keys keep in-frame order in the view, so position order == the reference's bucket order j.
+  // Two phases per batch of kInvUnroll x 256 entries, so that the expensive part runs with every lane busy:
+  //   1. each thread walks the table chains of its entries and queues the tag hits (entry, probe);
+  //   2. the queue is drained one hit per thread: exact key check, frame test, FP64 distance test.
+  const uint32_t cframe = (uint32_t)c.frame;
+  auto test_hit = [&](uint32_t p, uint32_t io, unsigned long long key) {
+    const uint32_t i = io >> 5;
+    const DescRec r = P.q[q0 + i];
+    if (probe_cell_key(r, (int)(io & 31u)) != key || r.frame == cframe) return;
+    const double *e = P.f_side + 3 * (fo + (int64_t)p);
+    const double d2 = sqn3(__dsub_rn(r.s[0], e[0]), __dsub_rn(r.s[1], e[1]), __dsub_rn(r.s[2], e[2]));
+    if (d2 < P.aux[q0 + i].thr2) {
+      const uint32_t at = atomicAdd(&s_n, 1u);
+      if (at < (uint32_t)kSortCap) {
+        s_rec[at] = (i << 17) | ((io & 31u) << 12) | p;
+        atomicAdd(&s_bin32[i >> 1], 1u << (16 * (i & 1u)));
+      }
+    }
+  };
   for (int pb = 0; pb < nf; pb += kInvUnroll * kCollectThreads) {
-    unsigned long long key[kInvUnroll], slot[kInvUnroll];
-    uint32_t pos[kInvUnroll];
+    unsigned long long key[kInvUnroll];
+    uint32_t slot[kInvUnroll], pos[kInvUnroll];
 #pragma unroll
     for (int u = 0; u < kInvUnroll; ++u) {
       const int p = pb + u * kCollectThreads + tid;
@@ -1317,34 +1433,30 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect_inv(CollectInvParam
     for (int u = 0; u < kInvUnroll; ++u) {
       const int p = pb + u * kCollectThreads + tid;
       if (slot[u] == kQtEmpty) continue;
-      const uint32_t tag = (uint32_t)(mix64(key[u]) >> 32);
-      bool have = false;
-      double e0 = 0, e1 = 0, e2 = 0;
-      unsigned long long sl = slot[u];
+      const uint32_t tag = qt_tag(mix64(key[u]));
+      uint32_t sl = slot[u];
       uint32_t ps = pos[u];
       while (sl != kQtEmpty) {
-        if ((uint32_t)(sl >> 32) == tag) {
-          const uint32_t io = (uint32_t)sl;
-          const DescRec r = P.q[q0 + (io >> 5)];
-          if (probe_cell_key(r, (int)(io & 31u)) == key[u] && r.frame != (uint32_t)c.frame) {
-            if (!have) { e0 = P.f_side[3 * (fo + p)]; e1 = P.f_side[3 * (fo + p) + 1]; e2 = P.f_side[3 * (fo + p) + 2]; have = true; }
-            const double d2 = sqn3(__dsub_rn(r.s[0], e0), __dsub_rn(r.s[1], e1), __dsub_rn(r.s[2], e2));
-            if (d2 < P.aux[q0 + (io >> 5)].thr2) {
-              const uint32_t at = atomicAdd(&s_n, 1u);
-              if (at < (uint32_t)kSortCap) {
-                const uint32_t i = io >> 5;
-                s_rec[at] = (i << 17) | ((io & 31u) << 12) | (uint32_t)p;
-                atomicAdd(&s_bin32[i >> 1], 1u << (16 * (i & 1u)));
-              }
-            }
-          }
+        if ((sl >> 18) == tag) {
+          const uint32_t io = sl & 0x3FFFFu;
+          const uint32_t at = atomicAdd(&s_qn, 1u);
+          if (at < (uint32_t)kSortCap) s_out[at] = (io << 12) | (uint32_t)p;
+          else test_hit((uint32_t)p, io, key[u]);  // queue full (degenerate geometry): decide in place
         }
         ps = (ps + 1) & mask;
         sl = __ldg(tk + ps);
       }
     }
+    __syncthreads();
+    const int nhit = (int)min(s_qn, (uint32_t)kSortCap);
+    for (int it = tid; it < nhit; it += kCollectThreads) {
+      const uint32_t item = s_out[it];
+      test_hit(item & 0xFFFu, item >> 12, P.f_key[fo + (int64_t)(item & 0xFFFu)]);
+    }
+    __syncthreads();
+    if (tid == 0) s_qn = 0;
+    __syncthreads();
   }
-  __syncthreads();
   const int n = (int)min(s_n, (uint32_t)c.nmatch);
   // ---- counting sort on the descriptor: exclusive scan of the counters ...
   {
@@ -1556,7 +1668,8 @@ __global__ void __launch_bounds__(128) k_hypotheses(VerifyParams P, int nslot) {
   for (int i = 0; i < 3; ++i) o[9 + i] = t[i];
 }
 
-__global__ void __launch_bounds__(kVerifyThreads, 5) k_verify(VerifyParams P) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kVerifyThreads, kMinBlocks) k_verify(VerifyParams P) {
   __shared__ __align__(16) double s_pose[kMaxHyp][12];  // exact (R,t) of every hypothesis
   __shared__ __align__(16) float s_posef[kMaxHyp][16];  // rounded to float: R0..R8, t0..t2, margin(|t|), pad
   // s_bits[h * T + w]: ballots of hypothesis h over warp tile w (couples 32w..32w+31): .x pairs 2c, .y pairs 2c+1
@@ -1859,13 +1972,15 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   // probes per descriptor, ~14 on average: load ~0.45, never full)
   int64_t max_dq = 1;
   for (int qi2 = 0; qi2 < nq; ++qi2) max_dq = std::max<int64_t>(max_dq, qb->off[qi2 + 1] - qb->off[qi2]);
-  uint32_t qt_ts = 64;
-  while ((int64_t)qt_ts < 32 * max_dq) qt_ts <<= 1;
+  uint32_t qt_ts = 64;  // stride of a query's table: worst case (27 probes per descriptor); the slots used are sized per query
+  while ((int64_t)qt_ts < 64 * std::min<int64_t>(max_dq, kInvMaxDesc)) qt_ts <<= 1;
   // all queries of the batch in one group: splitting the batch so that the tables stay L2-resident was
   // measured slower (too little parallelism per launch); option collect_group overrides for experiments
   const int qt_group = h->opt.collect_group > 0 ? h->opt.collect_group : std::max(nq, 1);
-  size_t o_qtk = o; o += al((size_t)qt_group * qt_ts * 8);
+  size_t o_qtk = o; o += al((size_t)qt_group * qt_ts * 4);
+  size_t o_qpr = o; o += al((size_t)std::max(nq, 1) * 4);
   size_t o_jc = o; o += al(64);
+  size_t o_plan = o; o += al(2 * (kPlanMax + 1) * 8);
   const bool run_join = join_mode && h->opt.join_impl != 1;
   size_t o_jd = o; o += run_join ? al((size_t)std::max<int64_t>(qb->n, 1) * sizeof(JoinDesc)) : 0;
   size_t o_pose = o; o += al((size_t)std::max(nq * k, 1) * kMaxHyp * 12 * sizeof(double));
@@ -1881,10 +1996,11 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   const double join_band = 2.5e-6 * (1.0 + 1.0 / h->c.rough);
   SGTD_CUDA(h, cudaEventRecord(ev[0], st));
   if (qb->n > 0) {
+    SGTD_CUDA(h, cudaMemsetAsync(S + o_qpr, 0, (size_t)nq * 4, st));
     k_qaux<<<(unsigned)((qb->n + 255) / 256), 256, 0, st>>>(qb->rec.p, qb->d_off.p, nq, qb->n, h->c.rough, aux,
                                                              sort_q ? (uint64_t *)(S + o_sk0) : nullptr, (uint32_t *)(S + o_si0),
                                                              run_join ? (JoinDesc *)(S + o_jd) : nullptr, join_band,
-                                                             (uint32_t)h->frame_lo(), r->votes.p, Fa);
+                                                             (uint32_t)h->frame_lo(), r->votes.p, Fa, (uint32_t *)(S + o_qpr));
     SGTD_LAUNCHED(h);
     if (sort_q) {
       SGTD_CUDA(h, cub::DeviceRadixSort::SortPairs(S + o_cubs, cubs, (uint64_t *)(S + o_sk0), (uint64_t *)(S + o_sk1),
@@ -1923,9 +2039,14 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
       // (nq/ngroups x F x 4 B) stay L2-resident while bucket tiles stream past them with evict-first
       // loads; measured optimum on B200 (126 MB L2): ~50 MB of rows per group.  More groups = fewer
       // probes per bucket run, so no more than needed.
-      int ngroups = (int)std::min<int64_t>(32, std::max<int64_t>(1, ((int64_t)nq * Fa * 4 + (56ll << 20) - 1) / (56ll << 20)));
-      if (h->opt.join_groups > 0) ngroups = h->opt.join_groups;
+      // keyframe parts (option join_parts): a pass covers the rows of one query group x one keyframe range,
+      // so a group can be `parts` times larger for the same L2 footprint and a bucket is streamed once per
+      // GROUP (each pass reads its own slice of it): the bucket traffic drops by `parts`
+      const int parts = std::max(1, std::min(4, h->opt.join_parts));
+      int ngroups = (int)std::min<int64_t>(kPlanMax, std::max<int64_t>(1, ((int64_t)nq * Fa * 4 / parts + (56ll << 20) - 1) / (56ll << 20)));
+      if (h->opt.join_groups > 0) ngroups = std::min(kPlanMax, h->opt.join_groups);
       E2.group_shift = (uint32_t)sbits; E2.group_div = (uint32_t)std::max(1, (nq + ngroups - 1) / ngroups);
+      ngroups = (nq + (int)E2.group_div - 1) / (int)E2.group_div;  // groups that exist
       int gbits = 0;
       while ((1 << gbits) < ngroups) ++gbits;
       k_probe_emit<<<grid, kVoteThreads, 0, st>>>(E2);
@@ -1946,6 +2067,20 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
         J.pack = h->v_pack.p; J.band = join_band;
         J.frame_lo = (uint32_t)h->frame_lo(); J.F = Fa; J.votes = r->votes.p;
         J.seg_counter = d_cursor + 1; J.counters = r->counters.p; J.slot_mask = (uint32_t)((1ull << sbits) - 1);
+        J.plan = (unsigned long long *)(S + o_plan); J.ngroups = ngroups; J.parts = parts; J.group_shift = (uint32_t)sbits;
+        if (!run_join) {
+          if (parts > 1 && h->v_cut_parts != parts) {
+            const uint64_t nslots = h->table_mask + 1;
+            SGTD_CUDA(h, h->v_cut.reserve((size_t)nslots * (parts - 1), st, false));
+            k_bucket_cuts<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(h->table.p, nslots, h->v_frame.p, parts,
+                                                                           (uint32_t)((Fa + parts - 1) / parts), h->v_cut.p);
+            SGTD_LAUNCHED(h);
+            h->v_cut_parts = parts;
+          }
+          J.cut = h->v_cut.p;
+          k_join_plan<<<1, 64, 0, st>>>(J.pkey, npairs, J.group_shift, ngroups, parts, (unsigned long long *)(S + o_plan));
+          SGTD_LAUNCHED(h);
+        }
         const int jgrid = h->sm_count * 4;
         if (h->opt.stats_unique) {
           const size_t words = ((size_t)h->table_mask + 32) / 32;
@@ -1957,8 +2092,9 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
         }
         if (!run_join) {
           SGTD_CUDA(h, cudaEventRecord(ev[8], st));
-          if (h->opt.debug_novote) k_vote_join<false><<<jgrid, kVoteThreads, 0, st>>>(J);
-          else { k_vote_join<true><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
+          if (h->opt.debug_novote) k_vote_join<false, false><<<jgrid, kVoteThreads, 0, st>>>(J);
+          else if (h->opt.join_hint) { k_vote_join<true, true><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
+          else { k_vote_join<true, false><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
           SGTD_LAUNCHED(h);
           SGTD_CUDA(h, cudaGetLastError());
         } else {
@@ -2037,7 +2173,7 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
       // per-query probe multimap, then one lookup per keyframe entry + shared-memory sort
       CollectInvParams I{};
       I.cands = r->cands.p; I.k = k; I.q = qb->rec.p; I.aux = aux; I.q_off = qb->d_off.p;
-      I.qt = (const unsigned long long *)(S + o_qtk); I.ts = qt_ts;
+      I.qt = (const uint32_t *)(S + o_qtk); I.stride = qt_ts; I.qprobes = (const uint32_t *)(S + o_qpr);
       I.frame_off = h->d_frame_off.p; I.f_key = h->f_key.p; I.f_g = h->f_g.p; I.f_side = h->f_side.p;
       I.frame_lo = h->frame_lo();
       I.m_q = r->m_q.p; I.m_g = r->m_g.p; I.m_cell = r->m_cell.p;
@@ -2047,8 +2183,8 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
                                         2 * kSortCap * 4 + 2 * kInvMaxDesc));
       for (int qb0 = 0; qb0 < nq; qb0 += qt_group) {
         const int gq = std::min(qt_group, nq - qb0);
-        k_query_index<<<gq, kIndexThreads, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (unsigned long long *)(S + o_qtk), qt_ts,
-                                                    r->cands.p, k);
+        k_query_index<<<gq, kIndexThreads, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (uint32_t *)(S + o_qtk), qt_ts,
+                                                    (const uint32_t *)(S + o_qpr), r->cands.p, k);
         I.q_base = qb0;
         k_collect_inv<<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
         h->launches += 2;
@@ -2071,7 +2207,8 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
     W.m_q = r->m_q.p; W.m_g = r->m_g.p; W.inl = r->inl.p; W.pose = (double *)(S + o_pose);
     k_hypotheses<<<(unsigned)(((size_t)nslot * kMaxHyp + 127) / 128), 128, 0, st>>>(W, (int)nslot);
     SGTD_LAUNCHED(h);
-    k_verify<<<(unsigned)nslot, kVerifyThreads, 0, st>>>(W);
+    if (h->opt.verify_impl == 1) k_verify<6><<<(unsigned)nslot, kVerifyThreads, 0, st>>>(W);
+    else k_verify<5><<<(unsigned)nslot, kVerifyThreads, 0, st>>>(W);
     SGTD_LAUNCHED(h);
     SGTD_CUDA(h, cudaGetLastError());
   }

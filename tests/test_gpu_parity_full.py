@@ -113,8 +113,10 @@ def test_100k_join_equals_exact_streaming_kernel(city100k):
     nf, nq = cfg["db"][2].shape[0] - 1, qo.shape[0] - 1
     qb = mgr.build(capi.make_nodes(qx, ql), qo)
     out = {}
-    for mode in ("join", "stream", "join_desc_collect", "join8", "join8_bulk_async"):
+    for mode in ("join", "stream", "join_desc_collect", "join8", "join8_bulk_async", "join_parts2", "join_parts4_hint"):
         mgr.set_option("vote_stream", mode == "stream")
+        mgr.set_option("join_parts", {"join_parts2": 2, "join_parts4_hint": 4}.get(mode, 0))
+        mgr.set_option("join_hint", mode == "join_parts4_hint")
         mgr.set_option("join_impl", {"join8": 0, "join8_bulk_async": 2}.get(mode, 1))
         mgr.set_option("collect_mode", 2 if mode == "join_desc_collect" else 0)
         res = mgr.search(qb)
@@ -125,7 +127,10 @@ def test_100k_join_equals_exact_streaming_kernel(city100k):
     mgr.set_option("vote_stream", 0)
     mgr.set_option("join_impl", 1)
     mgr.set_option("collect_mode", 0)
+    mgr.set_option("join_parts", 0)
+    mgr.set_option("join_hint", 0)
     assert out["join"] == out["stream"] == out["join_desc_collect"] == out["join8"] == out["join8_bulk_async"]
+    assert out["join"] == out["join_parts2"] == out["join_parts4_hint"]
     assert out["join"][1]["M"] > 4e9 and out["join"][1]["E"] > 1e10       # the bench workload's scale
 
 

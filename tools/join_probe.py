@@ -14,8 +14,9 @@ from sgtd_b200 import capi, synth  # noqa: E402
 def main():
     nkf = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
     nq = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
-    combos = sys.argv[3:] or ["join_impl=0", "join_impl=1", "join_impl=0,join_groups=6", "join_impl=0,join_groups=5",
-                              "join_impl=0,join_groups=4", "join_impl=0,join_groups=10", "join_impl=0,join_groups=16"]
+    combos = sys.argv[3:] or ["", "join_hint=1", "join_parts=2", "join_parts=2,join_hint=1", "join_parts=4",
+                              "join_parts=4,join_hint=1", "join_parts=2,join_groups=3", "join_parts=2,join_groups=6",
+                              "join_hint=1,join_groups=6", "join_hint=1,join_groups=5", "verify_impl=1"]
     cfg = synth.make_config(3, nkf, nq)
     xyz, lab, off = cfg["db"]
     qx, ql, qo = cfg["queries"]
@@ -27,12 +28,13 @@ def main():
         mgr.add(b); b.free()
     mgr.finalize()
     qb = mgr.build(capi.make_nodes(qx, ql), qo)
-    names = ("join_impl", "join_groups", "vote_stream", "collect_mode", "debug_novote")
+    names = ("join_impl", "join_groups", "vote_stream", "collect_mode", "debug_novote", "join_parts", "join_hint",
+             "verify_impl")
     crc0 = None
     for combo in combos:
         opts = dict(kv.split("=") for kv in combo.split(",") if kv)
         for k in names:
-            mgr.set_option(k, int(opts.get(k, 0)))
+            mgr.set_option(k, int(opts.get(k, 1 if k == "join_impl" else 0)))
         acc = {}
         for it in range(8):
             res = mgr.search(qb)
