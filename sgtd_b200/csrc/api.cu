@@ -232,13 +232,14 @@ int sgtd_set_option(sgtd_handle *h, const char *name, int32_t value) {
   else if (!strcmp(name, "join_parts")) h->opt.join_parts = (value >= 0 && value <= 4) ? (int)value : 0;
   else if (!strcmp(name, "join_hint")) h->opt.join_hint = value != 0;
   else if (!strcmp(name, "verify_impl")) h->opt.verify_impl = (int)value;
+  else if (!strcmp(name, "collect_unroll")) h->opt.collect_unroll = (int)value;
   else if (!strcmp(name, "join_impl")) {
     const int v = (value >= 0 && value <= 2) ? value : 1;
     if ((v == 1) != (h->opt.join_impl == 1)) h->dirty = true;  // 16-byte vs 8-byte entries: the index is rebuilt
     h->opt.join_impl = v;
   }
   else if (!strcmp(name, "stats_unique")) h->opt.stats_unique = value != 0;
-  else if (!strcmp(name, "s1_trace")) h->opt.s1_trace = value != 0;
+  else if (!strcmp(name, "s1_trace")) h->opt.s1_trace = (int)value;
   else if (!strcmp(name, "s1_variant")) h->opt.s1_variant = value == 1;
   else if (!strcmp(name, "s1_rows")) h->opt.s1_rows = value != 0;
   else if (!strcmp(name, "s1_replay")) h->opt.s1_replay = value == 1;

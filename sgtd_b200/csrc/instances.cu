@@ -154,7 +154,7 @@ __device__ __forceinline__ int table_lookup(const int *t_key, int mask, int voxe
 
 // ---- K3: polar transform, curved-voxel table, event list (one CTA per DCVC task) -------
 __global__ void __launch_bounds__(kS1Threads) k_dcvc_prepare(S1Buffers B, double startR, double deltaR, double deltaP,
-                                                              double deltaA) {
+                                                              double deltaA, int *t_fe_all) {
   __shared__ int s_warp[kS1Threads / 32];
   __shared__ double s_red[4][kS1Threads / 32];
   __shared__ double s_mm[4];
@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(kS1Threads) k_dcvc_prepare(S1Buffers B, double
       const int pos = B.slot[t.idx_off + r];
       const int which = (__ldcg(&t_min1[pos]) == r ? 1 : 0) | (__ldcg(&t_min2[pos]) == r ? 2 : 0);
       B.events[t.idx_off + base + p] = make_int4(r, pos, __ldcg(&t_coord[pos]), which);
+      if (which & 1) t_fe_all[t.tab_off + pos] = base + p;  // the voxel's name: index of its first seed event
     }
     base += total;
   }
@@ -379,7 +380,8 @@ __global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slo
   if (t.policy != P_DCVC) return;
   const TaskState ts = B.ts[blockIdx.x];
   const bool fits16 = ts.nvox + ts.ninvis < 65000;
-  if (kSmem) { if (!(ts.nvox > nvox_lo && ts.nvox <= nvox_hi && fits16) || ts.nevents <= cc_max_ev) return; }  // cc_max_ev: taken by k_dcvc_replay_cc
+  if (ts.nevents <= cc_max_ev) return;  // taken by k_dcvc_replay_cc
+  if (kSmem) { if (!(ts.nvox > nvox_lo && ts.nvox <= nvox_hi && fits16)) return; }
   else if (ts.nvox <= nvox_lo && fits16) return;
   const int tid = threadIdx.x, lane = tid & 31;
   const int height = ts.height, polarNum = ts.polarNum, width = ts.width;
@@ -591,27 +593,83 @@ __global__ void __launch_bounds__(kRpThreads) k_dcvc_replay(S1Buffers B, int slo
 // ---- K4b: component-parallel replay ---------------------------------------------------------------
 // Seed events only read and write the states of the seed's <= 27 neighbour voxels (and the labels living on
 // them), so events of different connected components of the voxel-neighbour graph commute; the only thing
-// they share is the counter that names new labels.  This form of the replay
-//   1. builds the shared-memory table and, per voxel, the index of its first event (as above);
-//   2. unions every voxel with its neighbour row (16-bit union-find over first-event indices, atomicCAS
-//      hooks the larger index under the smaller): components of the neighbour graph;
-//   3. hands the components to the CTA's 8 warps (greedy on the number of events, lightest warp first) and
-//      tags every event with its owner;
-//   4. lets all warps replay concurrently: a warp walks the event list with the same 32-wide windows as the
-//      sequential form, events of other warps count as skipped.  A new label is provisionally NAMED after the
-//      event that creates it (event index + 1); merges (parent[cur] = neigh) are structural, not by value;
-//   5. renames: the reference's label value is 1 + the number of label-creating events before it -- a prefix
-//      sum over the creation bitmap -- applied while the voxel states, the label forest and the labels of
-//      invisible seeds are written back.
-// Taken by tasks whose table fits the 2k / 8k / 16k-slot classes and that have at most kCcMaxEv events; the
-// rest go through the sequential forms.
+// they share is the counter that names new labels.  Two kernels:
+//   k_dcvc_rows   (fully parallel, all tasks) names every voxel after its FIRST seed event and writes, per
+//                 voxel, the row of its 27 neighbours (searchKNN order, :365-385) as such names -- the only
+//                 place the hash table is read;
+//   k_dcvc_replay_cc (one CTA of 8 warps per task; per-voxel state = 1-byte kind + 2-byte label in shared
+//                 memory, indexed by the voxel's name: no table in shared memory)
+//     1. unions every voxel with its row (16-bit union-find, atomicCAS hooks the larger name under the
+//        smaller): the components of the neighbour graph;
+//     2. hands the components to the warps (largest first, then greedily to the lightest warp, weight =
+//        events) and tags every event with its owner;
+//     3. lets all warps replay concurrently: a warp walks the event list with the same 32-wide windows as the
+//        sequential form, events of other warps count as skipped.  A new label is provisionally NAMED after
+//        the event that creates it (event index + 1); merges (parent[cur] = neigh) are structural;
+//     4. renames: the reference's label value is 1 + the number of label-creating events before it -- a
+//        prefix sum over the creation bitmap -- applied while the voxel states, the label forest and the
+//        labels of invisible seeds are written back.
+// Taken by tasks with at most kCcMaxEv events (three shared-memory classes by event count); the rest go
+// through the sequential forms above.
 constexpr int kCcThreads = 256;
 constexpr int kCcWarps = kCcThreads / 32;
-constexpr int kCcMaxEv = 8192;
+constexpr int kCcMaxEv = 16384;
 constexpr int kCcRing = 256;
+constexpr uint16_t kNoVox = 0xFFFFu;
+
+__global__ void __launch_bounds__(kS1Threads) k_dcvc_rows(S1Buffers B, const int *t_fe_all, uint16_t *rows_all) {
+  const Task t = B.tasks[blockIdx.x];
+  if (t.policy != P_DCVC) return;
+  const TaskState ts = B.ts[blockIdx.x];
+  const int nev = ts.nevents;
+  if (nev > kCcMaxEv) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int height = ts.height, polarNum = ts.polarNum, width = ts.width;
+  const int *t_key = B.t_key + t.tab_off, *t_fe = t_fe_all + t.tab_off;
+  const int gmask = t.tab_size - 1;
+  const int4 *events = B.events + t.idx_off;
+  int2 *evc = B.evc + t.idx_off;
+  uint16_t *rows = rows_all + (size_t)t.idx_off * 32;
+  for (int e0 = wid * 32; e0 < nev; e0 += kS1Threads) {
+    const int e = e0 + lane;
+    int4 ev = make_int4(0, 0, 0, 0);
+    if (e < nev) {
+      ev = events[e];
+      const int vis = (ev.z >> 21) <= height;
+      evc[e] = make_int2(__ldcg(t_fe + ev.y) | (ev.w << 28) | (vis << 30), ev.x);
+    }
+    unsigned firsts = __ballot_sync(0xffffffffu, e < nev && (ev.w & 1));
+    while (firsts) {
+      const int j = __ffs(firsts) - 1;
+      firsts &= firsts - 1;
+      const int c = __shfl_sync(0xffffffffu, ev.z, j);
+      const int az = c & 1023, po = (c >> 10) & 2047, pi = c >> 21;
+      uint16_t out = kNoVox;
+      if (lane < 27) {
+        const int z = pi - 1 + lane / 9, y = po - 1 + (lane / 3) % 3, x = az - 1 + lane % 3;
+        if (!(z < 0 || z > height) && !(y < 0 || y > polarNum)) {
+          int ax = x;
+          if (ax < 0) ax = width - 1;
+          if (ax > 300) ax = 300;
+          if (y < polarNum) {  // polar index polarNum is legal for the guard but never occupied
+            const int pos = table_lookup(t_key, gmask, (ax * (polarNum + 1) + y) + z * (polarNum + 1) * (width + 1));
+            if (pos >= 0) out = (uint16_t)__ldcg(t_fe + pos);
+          }
+        }
+      }
+      rows[(size_t)(e0 + j) * 32 + lane] = out;
+    }
+  }
+}
 
 __device__ __forceinline__ int uf16_find(volatile uint16_t *par, int x) {
-  while (true) { const int p = par[x]; if (p == x) return x; x = p; }
+  while (true) {
+    const int p = par[x];
+    if (p == x) return x;
+    const int g = par[p];
+    if (g != p) par[x] = (uint16_t)g;  // path halving; concurrent callers only move pointers towards the root
+    x = g;
+  }
 }
 __device__ __forceinline__ void uf16_unite(uint16_t *par, int a, int b) {
   while (true) {
@@ -622,116 +680,111 @@ __device__ __forceinline__ void uf16_unite(uint16_t *par, int a, int b) {
   }
 }
 
-__global__ void __launch_bounds__(kCcThreads) k_dcvc_replay_cc(S1Buffers B, int slots, int nvox_lo, int nvox_hi) {
+// cap: events the shared-memory arrays hold; tasks with nev_lo < nevents <= cap are taken
+__global__ void __launch_bounds__(kCcThreads) k_dcvc_replay_cc(S1Buffers B, const uint16_t *rows_all, int cap, int nev_lo) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ uint32_t s_new[kCcMaxEv / 32 + 1];  // bit e: event e created a label
   __shared__ uint32_t s_pre[kCcMaxEv / 32 + 1];  // labels created before word w
   __shared__ int s_tot[4];
+  __shared__ int s_wload[kCcWarps];
   const Task t = B.tasks[blockIdx.x];
   if (t.policy != P_DCVC) return;
   const TaskState ts = B.ts[blockIdx.x];
   const int nev = ts.nevents;
-  if (!(ts.nvox > nvox_lo && ts.nvox <= nvox_hi && nev <= kCcMaxEv)) return;
+  if (!(nev > nev_lo && nev <= cap)) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int height = ts.height, polarNum = ts.polarNum, width = ts.width;
-  VoxTable<true> T{};
-  T.w = reinterpret_cast<uint32_t *>(s_dyn); T.lab = reinterpret_cast<uint16_t *>(s_dyn + (size_t)slots * 4); T.mask = (uint32_t)slots - 1;
-  uint16_t *s_a = reinterpret_cast<uint16_t *>(s_dyn + (size_t)slots * 6);           // union-find of the components, then of the labels
-  uint16_t *s_b = s_a + (kCcMaxEv + 2);                                              // root of each event, then the warps' event rings
-  int2 *s_ring = reinterpret_cast<int2 *>(s_dyn + (size_t)slots * 6 + 2 * (size_t)(kCcMaxEv + 2) * 2);
-  int4 *events = B.events + t.idx_off;
+  // per voxel (named after its first event): label, kind; per event / label: union-find, root
+  uint16_t *s_lab = reinterpret_cast<uint16_t *>(s_dyn);
+  uint16_t *s_a = s_lab + cap;             // union-find of the components, then of the labels (index = label <= cap)
+  uint16_t *s_b = s_a + (cap + 2);         // component root of every event
+  int2 *s_ring = reinterpret_cast<int2 *>(s_b + cap + 2);  // (6 cap + 8 bytes: 8-byte aligned for cap % 4 == 0)
+  uint8_t *s_kind = reinterpret_cast<uint8_t *>(s_ring + kCcWarps * kCcRing);
+  const int4 *events = B.events + t.idx_off;
   int2 *evc = B.evc + t.idx_off;
   int *pt_label = B.pt_label + t.idx_off;
+  const uint16_t *rows = rows_all + (size_t)t.idx_off * 32;
   const long long c0 = clock64();
-  // ---- 1. table, first event of each voxel, replay form of the events
-  for (int i = tid; i < slots; i += kCcThreads) { T.w[i] = kVEmpty; T.lab[i] = 0; }
-  for (int i = tid; i <= kCcMaxEv / 32; i += kCcThreads) s_new[i] = 0;
+  for (int e = tid; e < nev; e += kCcThreads) { s_a[e] = (uint16_t)e; s_kind[e] = K_NONE; s_lab[e] = 0; }
+  const int nwords = (nev + 31) >> 5;
+  for (int i = tid; i <= nwords; i += kCcThreads) s_new[i] = 0;
   if (tid < 4) s_tot[tid] = 0;
+  if (tid < kCcWarps) s_wload[tid] = 0;
   __syncthreads();
-#pragma unroll 4
-  for (int e = tid; e < nev; e += kCcThreads) {
-    const int4 ev = events[e];
-    s_a[e] = (uint16_t)e;
-    if (!(ev.w & 1)) continue;
-    const int c = ev.z;
-    const uint32_t key = coord27(c & 1023, (c >> 10) & 2047, c >> 21);
-    uint32_t pos = hash_u32(key) & T.mask;
-    while (atomicCAS(&T.w[pos], kVEmpty, key) != kVEmpty) pos = (pos + 1) & T.mask;
-    T.lab[pos] = (uint16_t)e;
-  }
-  __syncthreads();
-  const long long c1 = clock64();
-  auto neighbour = [&](int slot) -> int {
-    const uint32_t c = T.w[slot] & kCoordMask;
-    const int az = c & 511, po = (c >> 9) & 1023, pi = c >> 19;
-    int nb = -1;
-    if (lane < 27) {
-      const int z = pi - 1 + lane / 9, y = po - 1 + (lane / 3) % 3, x = az - 1 + lane % 3;
-      if (!(z < 0 || z > height) && !(y < 0 || y > polarNum)) {
-        int ax = x;
-        if (ax < 0) ax = width - 1;
-        if (ax > 300) ax = 300;
-        if (y < polarNum) nb = T.lookup(ax, y, z);
-      }
-    }
-    return nb;
-  };
-  // ---- 2. own slot of every event; components: every voxel united with its neighbour row
+  // ---- 1. components: every voxel united with its neighbour row.  Warp-cooperative: the roots of the voxel
+  //         and of its neighbours are found in parallel, the smallest is the target and every other distinct
+  //         root is hooked under it with one CAS (a lost race falls back to the generic unite); the next
+  //         voxel's row is in flight meanwhile.
   for (int e0 = wid * 32; e0 < nev; e0 += kCcThreads) {
     const int e = e0 + lane;
-    int4 ev = make_int4(0, 0, 0, 0);
-    int slot = 0;
-    if (e < nev) {
-      ev = events[e];
-      const int c = ev.z;
-      slot = T.lookup(c & 1023, (c >> 10) & 2047, c >> 21);
-      const int vis = (c >> 21) <= height;
-      evc[e] = make_int2(slot | (ev.w << 28) | (vis << 30), ev.x);
-    }
-    unsigned firsts = __ballot_sync(0xffffffffu, e < nev && (ev.w & 1));
+    const int x = e < nev ? evc[e].x : 0;
+    unsigned firsts = __ballot_sync(0xffffffffu, e < nev && ((x >> 28) & 1));
     while (firsts) {
-      const int j = __ffs(firsts) - 1;
-      firsts &= firsts - 1;
-      const int nb = neighbour(__shfl_sync(0xffffffffu, slot, j));
-      if (nb >= 0) uf16_unite(s_a, e0 + j, (int)T.lab[nb]);
-      __syncwarp();
+      // up to kDepth voxels per trip: all their rows are requested before the first is used
+      constexpr int kDepth = 8;
+      int jj[kDepth];
+      uint16_t nbs[kDepth];
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u) {
+        jj[u] = firsts ? __ffs(firsts) - 1 : -1;
+        firsts &= firsts - 1;
+        nbs[u] = jj[u] >= 0 ? rows[(size_t)(e0 + jj[u]) * 32 + lane] : kNoVox;
+      }
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u) {
+        if (jj[u] < 0) break;
+        const int mine = nbs[u] != kNoVox ? (int)nbs[u] : e0 + jj[u];  // lanes without a neighbour stand in for the voxel itself
+        const int rk = uf16_find(s_a, mine);
+        const int m = (int)__reduce_min_sync(0xffffffffu, (unsigned)rk);
+        if (rk != m && atomicCAS(reinterpret_cast<unsigned short *>(s_a + rk), (unsigned short)rk, (unsigned short)m) != (unsigned short)rk)
+          uf16_unite(s_a, rk, m);
+      }
     }
   }
   __syncthreads();
-  // ---- 3. root and weight of every component, owners
-  for (int e = tid; e < nev; e += kCcThreads) s_b[e] = (uint16_t)uf16_find(s_a, (int)T.lab[evc[e].x & 0xFFFF]);
+  const long long c_union = clock64();
+  // ---- 2. root and weight of every component, owners
+  for (int e = tid; e < nev; e += kCcThreads) s_b[e] = (uint16_t)uf16_find(s_a, evc[e].x & 0xFFFF);
   __syncthreads();
   uint32_t *s_a32 = reinterpret_cast<uint32_t *>(s_a);
-  for (int i = tid; i < (kCcMaxEv + 2) / 2; i += kCcThreads) s_a32[i] = 0;
+  for (int i = tid; i < (nev + 2) / 2; i += kCcThreads) s_a32[i] = 0;
   __syncthreads();
-  for (int e = tid; e < nev; e += kCcThreads) { const uint32_t r = s_b[e]; atomicAdd(&s_a32[r >> 1], 1u << (16 * (r & 1u))); }  // <= 8192 per half
+  for (int e = tid; e < nev; e += kCcThreads) { const uint32_t r = s_b[e]; atomicAdd(&s_a32[r >> 1], 1u << (16 * (r & 1u))); }  // <= 16384 per half
   __syncthreads();
+  const long long c_wgt = clock64();
   if (wid == 0) {
     int load[kCcWarps];
 #pragma unroll
     for (int w = 0; w < kCcWarps; ++w) load[w] = 0;
-    for (int e0 = 0; e0 < nev; e0 += 32) {
-      const int e = e0 + lane;
-      unsigned roots = __ballot_sync(0xffffffffu, e < nev && s_b[e] == (uint16_t)e);
-      while (roots) {
-        const int j = __ffs(roots) - 1;
-        roots &= roots - 1;
-        const int wgt = s_a[e0 + j];
-        int best = 0;
+    // two passes: components with at least 1/16 of the events first (they decide the balance), then the rest
+    const int big = max(nev / 16, 1);
+    for (int pass = 0; pass < 2; ++pass)
+      for (int e0 = 0; e0 < nev; e0 += 32) {
+        const int e = e0 + lane;
+        const bool is_root = e < nev && s_b[e] == (uint16_t)e;
+        const int mine = is_root ? (int)s_a[e] : 0;
+        unsigned roots = __ballot_sync(0xffffffffu, is_root && ((pass == 0) == (mine >= big)));
+        while (roots) {
+          const int j = __ffs(roots) - 1;
+          roots &= roots - 1;
+          const int wgt = __shfl_sync(0xffffffffu, mine, j);
+          int best = 0;
 #pragma unroll
-        for (int w = 1; w < kCcWarps; ++w) if (load[w] < load[best]) best = w;
+          for (int w = 1; w < kCcWarps; ++w) if (load[w] < load[best]) best = w;
 #pragma unroll
-        for (int w = 0; w < kCcWarps; ++w) if (w == best) load[w] += wgt;
-        if (lane == 0) s_a[e0 + j] = (uint16_t)best;  // the root's entry now holds the owner
+          for (int w = 0; w < kCcWarps; ++w) if (w == best) load[w] += wgt;
+          if (lane == 0) s_lab[e0 + j] = (uint16_t)best;  // (s_lab is free until the replay starts)
+        }
       }
-    }
   }
   __syncthreads();
-  for (int e = tid; e < nev; e += kCcThreads) { int2 v = evc[e]; v.x |= (int)s_a[s_b[e]] << 16; evc[e] = v; }
+#pragma unroll 4
+  for (int e = tid; e < nev; e += kCcThreads) { int2 v = evc[e]; v.x |= (int)s_lab[s_b[e]] << 16; evc[e] = v; }
+  __syncthreads();
+  for (int e = tid; e < nev; e += kCcThreads) s_lab[e] = 0;
   __threadfence_block();
   __syncthreads();
-  const long long c2 = clock64();
-  // ---- 4. replay: every warp walks the whole event list and takes the seeds of its own components
+  const long long c1 = clock64();
+  // ---- 3. replay: every warp walks the whole event list and takes the seeds of its own components
   {
     uint16_t *lpar = s_a;  // label forest, indexed by the provisional label (creating event + 1)
     int2 *ring = s_ring + wid * kCcRing;
@@ -744,6 +797,7 @@ __global__ void __launch_bounds__(kCcThreads) k_dcvc_replay_cc(S1Buffers B, int 
         x = g;
       }
     };
+    auto set_vox = [&](int vx, int kind, int label) { s_kind[vx] = (uint8_t)kind; s_lab[vx] = (uint16_t)label; };
     int n_active = 0, n_windows = 0, n_labels = 0;
     int loaded = 0, pre_base = 0;
     int2 pre[4];
@@ -765,10 +819,10 @@ __global__ void __launch_bounds__(kCcThreads) k_dcvc_replay_cc(S1Buffers B, int 
       const int ei = e0 + lane;
       const bool valid = ei < nev;
       const int2 ew = valid ? ring[ei & (kCcRing - 1)] : make_int2(0, 0);
-      const int oslot = ew.x & 0xFFFF, owner = (ew.x >> 16) & 7, which = (ew.x >> 28) & 3, ovis = (ew.x >> 30) & 1;
+      const int ovox = ew.x & 0xFFFF, owner = (ew.x >> 16) & 7, which = (ew.x >> 28) & 3, ovis = (ew.x >> 30) & 1;
       bool skip = !valid || owner != wid;
       if (!skip && ovis) {
-        const int kd = T.kind(oslot);
+        const int kd = s_kind[ovox];
         skip = kd == K_ALL || (kd == K_NONE && !(which & 1)) || (kd == K_HEAD && !(which & 2));
       }
       const unsigned act = __ballot_sync(0xffffffffu, !skip);
@@ -777,12 +831,22 @@ __global__ void __launch_bounds__(kCcThreads) k_dcvc_replay_cc(S1Buffers B, int 
       ++n_active;
       const int a = __ffs(act) - 1;
       e0 += a + 1;
-      const int v = __shfl_sync(0xffffffffu, oslot, a), vis = __shfl_sync(0xffffffffu, ovis, a);
+      const int v = __shfl_sync(0xffffffffu, ovox, a), vis = __shfl_sync(0xffffffffu, ovis, a);
       const int r = __shfl_sync(0xffffffffu, ew.y, a);
       const int ea = e0 - 1;
-      const int nb = neighbour(v);
+      int nb = -1;
+      if (lane < 27) { const uint16_t x = rows[(size_t)v * 32 + lane]; nb = x == kNoVox ? -1 : (int)x; }
+      {
+        // rows of the seeds this warp may take next (its events among the 32 after this one): into L1 while
+        // this seed is walked
+        const int en = e0 + lane;
+        if (en < min(loaded, nev)) {
+          const int xn = ring[en & (kCcRing - 1)].x;
+          if (((xn >> 16) & 7) == wid) asm volatile("prefetch.global.L1 [%0];" ::"l"(rows + (size_t)(xn & 0xFFFF) * 32));
+        }
+      }
       int kd = K_NONE, lb = -1;
-      if (nb >= 0) T.get(nb, kd, lb);
+      if (nb >= 0) { kd = s_kind[nb]; lb = s_lab[nb]; }
       const bool labelled = nb >= 0 && kd != K_NONE;
       const unsigned Lm = __ballot_sync(0xffffffffu, labelled);
       int root = -1;
@@ -795,41 +859,44 @@ __global__ void __launch_bounds__(kCcThreads) k_dcvc_replay_cc(S1Buffers B, int 
         const int L = ea + 1;
         ++n_labels;
         if (lane == 0) { lpar[L] = (uint16_t)L; atomicOr(&s_new[ea >> 5], 1u << (ea & 31)); if (!vis) pt_label[r] = L; }
-        if (nb >= 0) T.set(nb, K_ALL, L);
+        if (nb >= 0) set_vox(nb, K_ALL, L);
       } else {
+        // chain the distinct roots in first-occurrence order: cur -> neigh (:323-327)
         const unsigned after = Fm & ~((2u << lane) - 1u);
         const int nroot = __shfl_sync(0xffffffffu, root, after ? __ffs(after) - 1 : lane);
         if (is_first && after) lpar[root] = (uint16_t)nroot;
         const int cur = __shfl_sync(0xffffffffu, root, 31 - __clz(Fm));
+        // an unlabelled neighbour takes the value `cur` has when the walk reaches it
         const unsigned before = Fm & ((1u << lane) - 1u);
         const int cprev = __shfl_sync(0xffffffffu, root, before ? 31 - __clz(before) : lane);
         const bool takes = nb >= 0 && kd == K_NONE && before;
-        if (takes) T.set(nb, K_ALL, cprev);
-        if (labelled && kd == K_HEAD) T.set_kind(nb, K_ALL);
+        if (takes) set_vox(nb, K_ALL, cprev);
+        if (labelled && kd == K_HEAD) s_kind[nb] = K_ALL;
         if (vis) {
           const unsigned self = __ballot_sync(0xffffffffu, nb == v && (takes || labelled));
-          if (!self && lane == 0) T.set(v, K_HEAD, cur);
+          // own voxel passed while cur == -1: only the seed point itself is labelled (:330-331)
+          if (!self && lane == 0) set_vox(v, K_HEAD, cur);
         } else if (lane == 0) {
           pt_label[r] = cur;
         }
       }
       __syncwarp();
     }
-    if (lane == 0) { atomicAdd(&s_tot[0], n_active); atomicAdd(&s_tot[1], n_windows); atomicAdd(&s_tot[2], n_labels); }
+    if (lane == 0) { atomicAdd(&s_tot[0], n_active); atomicAdd(&s_tot[1], n_windows); atomicAdd(&s_tot[2], n_labels); s_wload[wid] = n_active; }
   }
   __threadfence_block();
   __syncthreads();
-  const long long c3 = clock64();
-  // ---- 5. the reference's label values, write-back
+  const long long c2 = clock64();
+  // ---- 4. the reference's label values, write-back
   if (wid == 0) {
     int run = 0;
-    for (int w0 = 0; w0 <= kCcMaxEv / 32; w0 += 32) {
+    for (int w0 = 0; w0 <= nwords; w0 += 32) {
       const int w = w0 + lane;
-      const int cnt = (w <= kCcMaxEv / 32) ? __popc(s_new[w]) : 0;
+      const int cnt = (w <= nwords) ? __popc(s_new[w]) : 0;
       int inc = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
-      if (w <= kCcMaxEv / 32) s_pre[w] = (uint32_t)(run + inc - cnt);
+      if (w <= nwords) s_pre[w] = (uint32_t)(run + inc - cnt);
       run += __shfl_sync(0xffffffffu, inc, 31);
     }
   }
@@ -844,20 +911,23 @@ __global__ void __launch_bounds__(kCcThreads) k_dcvc_replay_cc(S1Buffers B, int 
     const int4 ev = events[e];
     const int2 ec = evc[e];
     if (ev.w & 1) {
-      int kd, lb;
-      T.get(ec.x & 0xFFFF, kd, lb);
-      g_kind[ev.y] = kd; g_label[ev.y] = kd == K_NONE ? -1 : final_label(lb);
+      const int kd = s_kind[e];
+      g_kind[ev.y] = kd; g_label[ev.y] = kd == K_NONE ? -1 : final_label((int)s_lab[e]);
     }
     if (!((ec.x >> 30) & 1)) pt_label[ec.y] = final_label(pt_label[ec.y]);
     if ((s_new[e >> 5] >> (e & 31)) & 1u) g_parent[final_label(e + 1)] = final_label((int)s_a[e + 1]);
   }
   if (tid == 0) {
     TaskState &o = B.ts[blockIdx.x];
-    o.labelCount = s_tot[2]; o.dbg_active = s_tot[0]; o.dbg_windows = s_tot[1];
-    o.dbg_cyc[0] = c1 - c0; o.dbg_cyc[1] = c2 - c1; o.dbg_cyc[2] = c3 - c2; o.dbg_cyc[3] = clock64() - c3;
+    int mx = 0;
+    for (int w = 0; w < kCcWarps; ++w) mx = max(mx, s_wload[w]);
+    o.labelCount = s_tot[2]; o.dbg_active = s_tot[0]; o.dbg_windows = mx;  // (windows field: seeds of the busiest warp)
+    // (trace fields: union | weights + owners + tagging | replay + renaming + write-back | of which owners + tagging)
+    o.dbg_cyc[0] = c_union - c0; o.dbg_cyc[1] = c1 - c_union; o.dbg_cyc[2] = clock64() - c1; o.dbg_cyc[3] = c1 - c_wgt;
+    (void)c2;
   }
 }
-constexpr size_t kCcExtraSmem = 2 * (size_t)(kCcMaxEv + 2) * 2 + (size_t)kCcWarps * kCcRing * sizeof(int2);
+static size_t cc_smem(int cap) { return (size_t)cap * 7 + 16 + (size_t)kCcWarps * kCcRing * sizeof(int2); }
 
 // ---- K5: final label per point, per-label size and first point, compact label list -------
 __global__ void __launch_bounds__(kS1Threads) k_s1_finish(S1Buffers B) {
@@ -1004,7 +1074,7 @@ struct S1Pool {
   DevBuf<int64_t> d_off; DevBuf<uint32_t> d_cnt; DevBuf<Task> d_tasks; DevBuf<TaskState> d_ts;
   DevBuf<int> d_pp, d_tab, d_lab, d_pool, d_map; DevBuf<double> d_polar, d_bounds; DevBuf<unsigned long long> d_cur;
   DevBuf<InstRec> d_inst; DevBuf<sgtd_node> d_nodes;
-  DevBuf<int> d_map2; DevBuf<uint32_t> d_sort; DevBuf<int64_t> d_seg; DevBuf<unsigned char> d_cub;
+  DevBuf<uint16_t> d_rows; DevBuf<int> d_map2; DevBuf<uint32_t> d_sort; DevBuf<int64_t> d_seg; DevBuf<unsigned char> d_cub;
   DevBuf<float4> in_pts; DevBuf<uint32_t> in_lab; DevBuf<int32_t> out_pi;  // staging of host inputs / outputs
   cudaStream_t side[4] = {}; cudaEvent_t ev[5] = {}; bool have_streams = false;  // concurrent replay classes
   ~S1Pool() {
@@ -1012,7 +1082,7 @@ struct S1Pool {
     d_off.release(); d_cnt.release(); d_tasks.release(); d_ts.release(); d_pp.release(); d_tab.release(); d_lab.release();
     d_pool.release(); d_map.release(); d_polar.release(); d_bounds.release(); d_cur.release(); d_inst.release();
     d_nodes.release(); in_pts.release(); in_lab.release(); out_pi.release();
-    d_map2.release(); d_sort.release(); d_seg.release(); d_cub.release();
+    d_rows.release(); d_map2.release(); d_sort.release(); d_seg.release(); d_cub.release();
   }
 };
 static void s1_pool_free(void *p) { delete static_cast<S1Pool *>(p); }
@@ -1111,7 +1181,8 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     S1_CUDA(cudaMemsetAsync(d_ts.p, 0, nt * sizeof(TaskState), st));
     S1_CUDA(d_pp.reserve((size_t)std::max<int64_t>(n_idx, 1) * (4 + 4 + 2), st, false));  // cls_idx, slot, pt_label, final | events (int4) | evc (int2)
     S1_CUDA(d_polar.reserve((size_t)std::max<int64_t>(n_idx, 1) * 3, st, false));
-    S1_CUDA(d_tab.reserve((size_t)std::max<int64_t>(n_tab, 1) * 6, st, false));  // key,min1,min2,coord,kind,label
+    S1_CUDA(d_tab.reserve((size_t)std::max<int64_t>(n_tab, 1) * 7, st, false));  // key,min1,min2,coord,kind,label,first event
+    if (h->opt.s1_replay == 0) S1_CUDA(sp.d_rows.reserve((size_t)std::max<int64_t>(n_idx, 1) * 32, st, false));  // neighbour rows, one per event slot
     S1_CUDA(d_lab.reserve((size_t)std::max<int64_t>(n_lab, 1) * 3, st, false));  // parent,count,first
     S1_CUDA(d_bounds.reserve((size_t)std::max<int64_t>(n_bnd, 1), st, false));
     S1_CUDA(d_pool.reserve((size_t)std::max<int64_t>(n_lab, 1) * 3, st, false));
@@ -1138,7 +1209,7 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     S1_CUDA(cudaMemsetAsync(d_cur.p, 0, 8, st));
     trace("alloc + fills");
     k_s1_gather<<<nt, kS1Threads, 0, st>>>(B);
-    k_dcvc_prepare<<<nt, kS1Threads, 0, st>>>(B, 0.35, 0.0004, 1.2, 1.2);  // get_json.cpp:205-208
+    k_dcvc_prepare<<<nt, kS1Threads, 0, st>>>(B, 0.35, 0.0004, 1.2, 1.2, d_tab.p + 6 * n_tab);  // get_json.cpp:205-208
     trace("gather + prepare");
     {
       // table classes of the replay: every class is launched over all tasks, a CTA leaves at once unless its
@@ -1154,21 +1225,33 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
       S1_CUDA(cudaEventRecord(sp.ev[0], st));
       int lo = -1;
       const bool force_global = h->opt.s1_table == 1;  // tests: every task through the global-memory form
-      // default: the component-parallel form for the three smaller classes (option s1_replay = 1: sequential forms only)
-      const bool use_cc = h->opt.s1_replay == 0;
-      if (use_cc) S1_CUDA(cudaFuncSetAttribute(k_dcvc_replay_cc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSlots[2] * 6 + kCcExtraSmem)));
+      // default: the component-parallel form for every task with at most kCcMaxEv events (three shared-memory
+      // classes by event count, on their own streams); option s1_replay = 1: sequential forms only
+      const bool use_cc = h->opt.s1_replay == 0 && !force_global;
+      static const int kCaps[3] = {2048, 8192, kCcMaxEv};
+      if (use_cc) {
+        S1_CUDA(cudaFuncSetAttribute(k_dcvc_replay_cc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc_smem(kCaps[2])));
+        k_dcvc_rows<<<nt, kS1Threads, 0, st>>>(B, d_tab.p + 6 * n_tab, sp.d_rows.p);
+        S1_CUDA(cudaEventRecord(sp.ev[0], st));
+        int nlo = -1;
+        for (int c = 0; c < 3; ++c) {
+          S1_CUDA(cudaStreamWaitEvent(sp.side[c], sp.ev[0], 0));
+          k_dcvc_replay_cc<<<nt, kCcThreads, cc_smem(kCaps[c]), sp.side[c]>>>(B, sp.d_rows.p, kCaps[c], nlo);
+          nlo = kCaps[c];
+        }
+        h->launches += 4;
+      }
+      const int cc_max = use_cc ? kCcMaxEv : -1;
       for (int c = 0; c < 4 && !force_global; ++c) {
         const int hi = kSlots[c] * 3 / 10;  // load factor <= 0.3
         cudaStream_t sc = sp.side[c];
         S1_CUDA(cudaStreamWaitEvent(sc, sp.ev[0], 0));
-        const bool cc = use_cc && c < 3;
-        if (cc) k_dcvc_replay_cc<<<nt, kCcThreads, (size_t)kSlots[c] * 6 + kCcExtraSmem, sc>>>(B, kSlots[c], lo, hi);
-        k_dcvc_replay<true><<<nt, kRpThreads, (size_t)kSlots[c] * 6, sc>>>(B, kSlots[c], lo, hi, h->opt.s1_rows, cc ? kCcMaxEv : -1);
+        k_dcvc_replay<true><<<nt, kRpThreads, (size_t)kSlots[c] * 6, sc>>>(B, kSlots[c], lo, hi, h->opt.s1_rows, cc_max);
         S1_CUDA(cudaEventRecord(sp.ev[1 + c], sc));
         lo = hi;
       }
       // the global form (tables too large for shared memory; rare) looks its rows up itself
-      k_dcvc_replay<false><<<nt, kRpThreads, 0, st>>>(B, 0, lo, 0x7fffffff, 0, -1);
+      k_dcvc_replay<false><<<nt, kRpThreads, 0, st>>>(B, 0, lo, 0x7fffffff, 0, cc_max);
       if (!force_global)
         for (int c = 0; c < 4; ++c) S1_CUDA(cudaStreamWaitEvent(st, sp.ev[1 + c], 0));
     }
@@ -1187,7 +1270,7 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
       std::vector<int> ord(nt);
       for (int i = 0; i < nt; ++i) ord[i] = i;
       std::sort(ord.begin(), ord.end(), [&](int a, int b) { return ts[a].dbg_cyc[2] > ts[b].dbg_cyc[2]; });
-      for (int j = 0; j < std::min(nt, 6); ++j) {
+      for (int j = 0; j < (h->opt.s1_trace >= 2 ? nt : std::min(nt, 6)); ++j) {
         const TaskState &x = ts[ord[j]];
         fprintf(stderr, "[s1] task %4d cls %2d npts %6d nev %6d nvox %5d labels %5d active %5d windows %5d | kcyc build %lld transl %lld replay %lld wb %lld\n",
                 ord[j], tasks[ord[j]].cls, tasks[ord[j]].npts, x.nevents, x.nvox, x.labelCount, x.dbg_active, x.dbg_windows,

@@ -449,18 +449,20 @@ __device__ __forceinline__ void red_inc_if_keep(uint32_t *addr, bool hit, uint64
 }
 
 static_assert(kVoteUnroll == 4, "k_vote_join pairs the entries of a trip as (0,1) and (2,3)");
-// kHint: REDs carry an L2 evict-last policy
-template <bool kDoVote, bool kHint>
+// kHint: REDs carry an L2 evict-last policy; kParts: passes over keyframe-range parts (option join_parts)
+template <bool kDoVote, bool kHint, bool kParts>
 __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
   __shared__ double sh_s[kVoteThreads / 32][kJoinSeg][4];  // s0, s1, s2, thr2 of each probe of the segment (exact path)
   __shared__ float4 sh_f[kVoteThreads / 32][kJoinSeg];     // float s0, s1, s2, -thr2
   __shared__ uint4 sh_g[kVoteThreads / 32][kJoinSeg];      // band half-width w (float bits), query frame id, vote row pointer
   __shared__ unsigned long long sh_plan[2 * (kPlanMax + 1)];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 2 * (kPlanMax + 1); i += kVoteThreads) sh_plan[i] = P.plan[i];
-  __syncthreads();
+  if (kParts) {
+    for (int i = threadIdx.x; i < 2 * (kPlanMax + 1); i += kVoteThreads) sh_plan[i] = P.plan[i];
+    __syncthreads();
+  }
   const unsigned long long *g_first = sh_plan, *g_ticket = sh_plan + kPlanMax + 1;
-  const unsigned long long ntickets = g_ticket[P.ngroups];
+  const unsigned long long ntickets = kParts ? g_ticket[P.ngroups] : (P.npairs + kJoinSeg - 1) / kJoinSeg;
   const f32x2 negzero2 = pack2(-0.f, -0.f);
   uint64_t policy = 0;
   if (kHint) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
@@ -470,14 +472,22 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
     if (lane == 0) tk = atomicAdd(P.seg_counter, 1ull);
     tk = __shfl_sync(0xffffffffu, tk, 0);
     if (tk >= ntickets) break;
-    // ticket -> (query group, keyframe part, segment of the group)
-    const int grp = __popc(__ballot_sync(0xffffffffu, lane < P.ngroups && g_ticket[lane + 1] <= tk));
-    const unsigned long long gp0 = g_first[grp], gp1 = g_first[grp + 1];
-    const uint32_t gseg = (uint32_t)((gp1 - gp0 + kJoinSeg - 1) / kJoinSeg);  // < 2^32 pairs per batch
-    const uint32_t rel = (uint32_t)(tk - g_ticket[grp]);
-    const int part = (P.parts > 1) ? (int)(rel / gseg) : 0;
-    const unsigned long long p0 = gp0 + (unsigned long long)(rel - (uint32_t)part * gseg) * kJoinSeg;
-    const int np = (int)min((unsigned long long)kJoinSeg, gp1 - p0);
+    unsigned long long p0;
+    int np, part = 0;
+    if (kParts) {
+      // ticket -> (query group, keyframe part, segment of the group)
+      const int grp = __popc(__ballot_sync(0xffffffffu, lane < P.ngroups && g_ticket[lane + 1] <= tk));
+      const unsigned long long gp0 = g_first[grp], gp1 = g_first[grp + 1];
+      const uint32_t gseg = (uint32_t)((gp1 - gp0 + kJoinSeg - 1) / kJoinSeg);  // < 2^32 pairs per batch
+      const uint32_t rel = (uint32_t)(tk - g_ticket[grp]);
+      part = (int)(rel / gseg);
+      p0 = gp0 + (unsigned long long)(rel - (uint32_t)part * gseg) * kJoinSeg;
+      np = (int)min((unsigned long long)kJoinSeg, gp1 - p0);
+    } else {
+      // segments of kJoinSeg consecutive pairs (sorted by group, then bucket: the groups follow each other)
+      p0 = tk * kJoinSeg;
+      np = (int)min((unsigned long long)kJoinSeg, P.npairs - p0);
+    }
     uint32_t slot = 0xFFFFFFFFu;
     __syncwarp();
     if (lane < np) {
@@ -500,7 +510,7 @@ __global__ void __launch_bounds__(kVoteThreads, 4) k_vote_join(JoinParams P) {
       const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(&P.table[cur & P.slot_mask]));
       const uint32_t o = raw.z;
       uint32_t n = raw.w, e_lo = 0;  // this pass streams entries [e_lo, n) of the bucket: its keyframe part
-      if (P.parts > 1) {
+      if (kParts) {
         const uint32_t *c = P.cut + (size_t)(cur & P.slot_mask) * (uint32_t)(P.parts - 1);
         if (part > 0) e_lo = __ldg(c + part - 1);
         if (part < P.parts - 1) n = __ldg(c + part);
@@ -1371,7 +1381,8 @@ constexpr int kInvUnroll = 4;  // keyframe entries a thread looks up at a time (
 
 // dynamic shared memory: records [kSortCap] u32, sorted records [kSortCap] u32, per-descriptor
 // counters / offsets [bins] u16 (updated two per 32-bit atomic)
-__global__ void __launch_bounds__(kCollectThreads) k_collect_inv(CollectInvParams P) {
+template <int kHitUnroll>
+__global__ void __launch_bounds__(kCollectThreads, kHitUnroll >= 4 ? 2 : (kHitUnroll == 2 ? 3 : 4)) k_collect_inv(CollectInvParams P) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   uint32_t *s_rec = reinterpret_cast<uint32_t *>(s_dyn);
   uint32_t *s_out = s_rec + kSortCap;
@@ -1449,9 +1460,41 @@ __global__ void __launch_bounds__(kCollectThreads) k_collect_inv(CollectInvParam
     }
     __syncthreads();
     const int nhit = (int)min(s_qn, (uint32_t)kSortCap);
-    for (int it = tid; it < nhit; it += kCollectThreads) {
-      const uint32_t item = s_out[it];
-      test_hit(item & 0xFFFu, item >> 12, P.f_key[fo + (int64_t)(item & 0xFFFu)]);
+    // kHitUnroll hits per thread and trip: every load of all of them is issued before the first test
+    for (int it0 = 0; it0 < nhit; it0 += kHitUnroll * kCollectThreads) {
+      uint32_t item[kHitUnroll];
+      DescRec r[kHitUnroll];
+      unsigned long long fk[kHitUnroll];
+      double e0[kHitUnroll], e1[kHitUnroll], e2[kHitUnroll], thr2[kHitUnroll];
+#pragma unroll
+      for (int u = 0; u < kHitUnroll; ++u) {
+        const int it = it0 + u * kCollectThreads + tid;
+        item[u] = it < nhit ? s_out[it] : 0xFFFFFFFFu;
+      }
+#pragma unroll
+      for (int u = 0; u < kHitUnroll; ++u) {
+        if (item[u] == 0xFFFFFFFFu) continue;  // (a real item has descriptor < 8192: never all ones)
+        const uint32_t p = item[u] & 0xFFFu, i = item[u] >> 17;
+        r[u] = P.q[q0 + i];
+        fk[u] = P.f_key[fo + (int64_t)p];
+        const double *e = P.f_side + 3 * (fo + (int64_t)p);
+        e0[u] = e[0]; e1[u] = e[1]; e2[u] = e[2];
+        thr2[u] = P.aux[q0 + i].thr2;
+      }
+#pragma unroll
+      for (int u = 0; u < kHitUnroll; ++u) {
+        if (item[u] == 0xFFFFFFFFu) continue;
+        const uint32_t p = item[u] & 0xFFFu, io = item[u] >> 12, i = io >> 5;
+        if (probe_cell_key(r[u], (int)(io & 31u)) != fk[u] || r[u].frame == cframe) continue;
+        const double d2 = sqn3(__dsub_rn(r[u].s[0], e0[u]), __dsub_rn(r[u].s[1], e1[u]), __dsub_rn(r[u].s[2], e2[u]));
+        if (d2 < thr2[u]) {
+          const uint32_t at = atomicAdd(&s_n, 1u);
+          if (at < (uint32_t)kSortCap) {
+            s_rec[at] = (i << 17) | ((io & 31u) << 12) | p;
+            atomicAdd(&s_bin32[i >> 1], 1u << (16 * (i & 1u)));
+          }
+        }
+      }
     }
     __syncthreads();
     if (tid == 0) s_qn = 0;
@@ -2068,8 +2111,8 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
         J.frame_lo = (uint32_t)h->frame_lo(); J.F = Fa; J.votes = r->votes.p;
         J.seg_counter = d_cursor + 1; J.counters = r->counters.p; J.slot_mask = (uint32_t)((1ull << sbits) - 1);
         J.plan = (unsigned long long *)(S + o_plan); J.ngroups = ngroups; J.parts = parts; J.group_shift = (uint32_t)sbits;
-        if (!run_join) {
-          if (parts > 1 && h->v_cut_parts != parts) {
+        if (!run_join && parts > 1) {
+          if (h->v_cut_parts != parts) {
             const uint64_t nslots = h->table_mask + 1;
             SGTD_CUDA(h, h->v_cut.reserve((size_t)nslots * (parts - 1), st, false));
             k_bucket_cuts<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(h->table.p, nslots, h->v_frame.p, parts,
@@ -2092,9 +2135,11 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
         }
         if (!run_join) {
           SGTD_CUDA(h, cudaEventRecord(ev[8], st));
-          if (h->opt.debug_novote) k_vote_join<false, false><<<jgrid, kVoteThreads, 0, st>>>(J);
-          else if (h->opt.join_hint) { k_vote_join<true, true><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
-          else { k_vote_join<true, false><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
+          if (h->opt.debug_novote) k_vote_join<false, false, false><<<jgrid, kVoteThreads, 0, st>>>(J);
+          else if (parts > 1 && h->opt.join_hint) { k_vote_join<true, true, true><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
+          else if (parts > 1) { k_vote_join<true, false, true><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
+          else if (h->opt.join_hint) { k_vote_join<true, true, false><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
+          else { k_vote_join<true, false, false><<<jgrid, kVoteThreads, 0, st>>>(J); m_by_topk = true; }
           SGTD_LAUNCHED(h);
           SGTD_CUDA(h, cudaGetLastError());
         } else {
@@ -2179,14 +2224,21 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
       I.m_q = r->m_q.p; I.m_g = r->m_g.p; I.m_cell = r->m_cell.p;
       // shared memory of a candidate CTA: two record arrays + one 16-bit counter per query descriptor
       const size_t inv_smem = 2 * (size_t)kSortCap * 4 + 4 * (size_t)((std::min<int64_t>(max_dq, kInvMaxDesc) + 1) / 2);
-      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        2 * kSortCap * 4 + 2 * kInvMaxDesc));
+      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        2 * kSortCap * 4 + 2 * kInvMaxDesc));
+      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         2 * kSortCap * 4 + 2 * kInvMaxDesc));
       for (int qb0 = 0; qb0 < nq; qb0 += qt_group) {
         const int gq = std::min(qt_group, nq - qb0);
         k_query_index<<<gq, kIndexThreads, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (uint32_t *)(S + o_qtk), qt_ts,
                                                     (const uint32_t *)(S + o_qpr), r->cands.p, k);
         I.q_base = qb0;
-        k_collect_inv<<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
+        // (measured on the bench workload: 1 hit per thread and trip 5.0 ms, 2: 5.6, 4: 7.2 -- occupancy wins)
+        if (h->opt.collect_unroll == 4) k_collect_inv<4><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
+        else if (h->opt.collect_unroll == 2) k_collect_inv<2><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
+        else k_collect_inv<1><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
         h->launches += 2;
       }
     }

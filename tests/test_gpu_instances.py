@@ -21,10 +21,14 @@ def compare(mgr, orc, pts, lab):
     return nodes, r
 
 
-# replay forms: shared-memory voxel table with neighbour rows produced ahead by helper warps (default), the
-# same with the replaying warp doing its own lookups, and the global-memory table every task falls back to
-# when its table does not fit shared memory (forced here so that ordinary scans exercise it)
-FORMS = {"smem+rows": dict(s1_rows=1, s1_table=0), "smem": dict(s1_rows=0, s1_table=0), "global": dict(s1_rows=1, s1_table=1)}
+# replay forms: the component-parallel replay (default: components of the voxel-neighbour graph replayed
+# concurrently by the warps of a CTA, labels renamed afterwards); the sequential forms it falls back to for
+# oversized tasks -- shared-memory voxel table with neighbour rows produced ahead by helper warps, the same
+# with the replaying warp doing its own lookups, and the global-memory table (forced here so that ordinary
+# scans exercise them)
+FORMS = {"components": dict(s1_replay=0, s1_rows=1, s1_table=0),
+         "smem+rows": dict(s1_replay=1, s1_rows=1, s1_table=0), "smem": dict(s1_replay=1, s1_rows=0, s1_table=0),
+         "global": dict(s1_replay=1, s1_rows=1, s1_table=1)}
 
 
 @pytest.fixture(scope="module", params=list(FORMS))

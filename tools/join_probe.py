@@ -29,7 +29,7 @@ def main():
     mgr.finalize()
     qb = mgr.build(capi.make_nodes(qx, ql), qo)
     names = ("join_impl", "join_groups", "vote_stream", "collect_mode", "debug_novote", "join_parts", "join_hint",
-             "verify_impl")
+             "verify_impl", "collect_unroll")
     crc0 = None
     for combo in combos:
         opts = dict(kv.split("=") for kv in combo.split(",") if kv)

@@ -23,8 +23,9 @@ for i in sel:
     pts.append(p); labs.append(l.to(torch.int32)); off.append(off[-1] + p.shape[0])
 pts, labs, off = torch.cat(pts).contiguous(), torch.cat(labs).contiguous(), np.array(off, np.int64)
 mgr = capi.STDescManager(device=0)
+mgr.set_option("s1_replay", int(os.environ.get("S1_REPLAY", "0")))
 for it in range(reps):
-    mgr.set_option("s1_trace", 1 if it == reps - 1 and os.environ.get("S1_TRACE") else 0)
+    mgr.set_option("s1_trace", int(os.environ.get("S1_TRACE", "0")) if it == reps - 1 else 0)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     nodes, noff, ninst = mgr.extract_instances_ptr(pts.data_ptr(), labs.data_ptr(), off)
