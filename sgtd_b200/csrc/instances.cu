@@ -107,8 +107,9 @@ __global__ void k_s1_hist(const uint32_t *labels, const int64_t *scan_off, uint3
   }
 }
 
+template <int kThreads = kS1Threads>
 __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total) {
-  // exclusive scan over the 256 threads of the block (in thread order)
+  // exclusive scan over the kThreads threads of the block (in thread order)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = v;
 #pragma unroll
@@ -118,7 +119,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total) {
   __syncthreads();
   int base = 0; total = 0;
 #pragma unroll
-  for (int w = 0; w < kS1Threads / 32; ++w) { if (w < warp) base += s_warp[w]; total += s_warp[w]; }
+  for (int w = 0; w < kThreads / 32; ++w) { if (w < warp) base += s_warp[w]; total += s_warp[w]; }
   return base + incl - v;
 }
 
@@ -126,13 +127,26 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total) {
 __global__ void __launch_bounds__(kS1Threads) k_s1_gather(S1Buffers B) {
   __shared__ int s_warp[kS1Threads / 32];
   const Task t = B.tasks[blockIdx.x];
+  constexpr int kPer = 8;  // consecutive points per thread and trip: one block scan per 2,048 points
   int base = 0;
-  for (int i0 = 0; i0 < t.npts_scan; i0 += kS1Threads) {
-    const int i = i0 + threadIdx.x;
-    const int hit = (i < t.npts_scan) && ((B.labels[t.pt0 + i] & 0xFFFFu) == (uint32_t)t.cls);
+  for (int i0 = 0; i0 < t.npts_scan; i0 += kS1Threads * kPer) {
+    const int i = i0 + threadIdx.x * kPer;
+    unsigned hits = 0;
+    if (i + kPer <= t.npts_scan && (reinterpret_cast<uintptr_t>(B.labels + t.pt0 + i) & 15) == 0) {  // two 16-byte loads
+      const uint4 a = *reinterpret_cast<const uint4 *>(B.labels + t.pt0 + i), b = *reinterpret_cast<const uint4 *>(B.labels + t.pt0 + i + 4);
+      const uint32_t l[kPer] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) hits |= (unsigned)((l[k] & 0xFFFFu) == (uint32_t)t.cls) << k;
+    } else {
+#pragma unroll
+      for (int k = 0; k < kPer; ++k)
+        if (i + k < t.npts_scan) hits |= (unsigned)((B.labels[t.pt0 + i + k] & 0xFFFFu) == (uint32_t)t.cls) << k;
+    }
     int total;
-    const int pos = block_excl_scan(hit, s_warp, total);
-    if (hit) B.cls_idx[t.idx_off + base + pos] = i;
+    int pos = base + block_excl_scan(__popc(hits), s_warp, total);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      if ((hits >> k) & 1u) B.cls_idx[t.idx_off + pos++] = i + k;
     base += total;
   }
 }
@@ -153,20 +167,24 @@ __device__ __forceinline__ int table_lookup(const int *t_key, int mask, int voxe
 }
 
 // ---- K3: polar transform, curved-voxel table, event list (one CTA per DCVC task) -------
-__global__ void __launch_bounds__(kS1Threads) k_dcvc_prepare(S1Buffers B, double startR, double deltaR, double deltaP,
-                                                              double deltaA, int *t_fe_all) {
-  __shared__ int s_warp[kS1Threads / 32];
-  __shared__ double s_red[4][kS1Threads / 32];
+// kThreads: 256 for tasks of up to kPrepSplit points, 1024 for larger ones (the loops are latency bound and the
+// largest task of a batch is the kernel's critical path)
+constexpr int kPrepSplit = 4096;
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) k_dcvc_prepare(S1Buffers B, double startR, double deltaR, double deltaP,
+                                                            double deltaA, int *t_fe_all) {
+  __shared__ int s_warp[kThreads / 32];
+  __shared__ double s_red[4][kThreads / 32];
   __shared__ double s_mm[4];
   __shared__ int s_grid[3];
   const Task t = B.tasks[blockIdx.x];
-  if (t.policy != P_DCVC) return;
+  if (t.policy != P_DCVC || (kThreads == kS1Threads) != (t.npts <= kPrepSplit)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double kPi = 3.14159265358979323846;  // M_PI
   double *polar = B.polar + 3 * t.idx_off;
   // 1. convert2polar (cluster_manager.hpp:172-206); running min/max start at 0,0,5,5 (:482-485)
   double mnP = 0.0, mxP = 0.0, mnR = 5.0, mxR = 5.0;
-  for (int r = tid; r < t.npts; r += kS1Threads) {
+  for (int r = tid; r < t.npts; r += kThreads) {
     const float4 p = B.pts[t.pt0 + B.cls_idx[t.idx_off + r]];
     const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
     const double rng = sqrt(__dadd_rn(__dmul_rn(x, x), __dadd_rn(__dmul_rn(y, y), __dmul_rn(z, z))));  // Eigen norm(): e0 + (e1 + e2)
@@ -189,7 +207,7 @@ __global__ void __launch_bounds__(kS1Threads) k_dcvc_prepare(S1Buffers B, double
   if (lane == 0) { s_red[0][warp] = mnP; s_red[1][warp] = mxP; s_red[2][warp] = mnR; s_red[3][warp] = mxR; }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < kS1Threads / 32; ++w) {
+    for (int w = 1; w < kThreads / 32; ++w) {
       s_red[0][0] = fmin(s_red[0][0], s_red[0][w]); s_red[1][0] = fmax(s_red[1][0], s_red[1][w]);
       s_red[2][0] = fmin(s_red[2][0], s_red[2][w]); s_red[3][0] = fmax(s_red[3][0], s_red[3][w]);
     }
@@ -219,7 +237,7 @@ __global__ void __launch_bounds__(kS1Threads) k_dcvc_prepare(S1Buffers B, double
   int *t_coord = B.t_coord + t.tab_off;
   const int mask = t.tab_size - 1;
   // 2. createHashTable (:224-252): voxel index of every point, table insert, lowest point per voxel
-  for (int r = tid; r < t.npts; r += kS1Threads) {
+  for (int r = tid; r < t.npts; r += kThreads) {
     const double rng = polar[3 * r], pitch = polar[3 * r + 1], az = polar[3 * r + 2];
     // getPolarIndex (:259-264): first r with radius < bounds[r]; bounds are increasing here
     int lo = 0, hi = polarNum;
@@ -239,14 +257,14 @@ __global__ void __launch_bounds__(kS1Threads) k_dcvc_prepare(S1Buffers B, double
     B.slot[t.idx_off + r] = (int)pos;
   }
   __syncthreads();
-  for (int r = tid; r < t.npts; r += kS1Threads) {
+  for (int r = tid; r < t.npts; r += kThreads) {
     const int pos = B.slot[t.idx_off + r];
     if (__ldcg(&t_min1[pos]) != r) atomicMin(&t_min2[pos], r);
   }
   __syncthreads();
   // 3. seed events in point order: two lowest points of a visible voxel, every point of an invisible one
   int base = 0;
-  for (int r0 = 0; r0 < t.npts; r0 += kS1Threads) {
+  for (int r0 = 0; r0 < t.npts; r0 += kThreads) {
     const int r = r0 + tid;
     int ev = 0;
     if (r < t.npts) {
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(kS1Threads) k_dcvc_prepare(S1Buffers B, double
       ev = !visible || __ldcg(&t_min1[pos]) == r || __ldcg(&t_min2[pos]) == r;
     }
     int total;
-    const int p = block_excl_scan(ev, s_warp, total);
+    const int p = block_excl_scan<kThreads>(ev, s_warp, total);
     if (ev) {
       const int pos = B.slot[t.idx_off + r];
       const int which = (__ldcg(&t_min1[pos]) == r ? 1 : 0) | (__ldcg(&t_min2[pos]) == r ? 2 : 0);
@@ -268,11 +286,11 @@ __global__ void __launch_bounds__(kS1Threads) k_dcvc_prepare(S1Buffers B, double
   if (tid == 0) B.ts[blockIdx.x].nevents = base;
   // 4. voxel and invisible-seed counts (the replay picks its table class from them)
   int nv = 0, ni = 0;
-  for (int sidx = tid; sidx < t.tab_size; sidx += kS1Threads) nv += __ldcg(&t_key[sidx]) != kEmptyVoxel;
-  for (int r = tid; r < t.npts; r += kS1Threads) ni += (__ldcg(&t_coord[B.slot[t.idx_off + r]]) >> 21) > height;
+  for (int sidx = tid; sidx < t.tab_size; sidx += kThreads) nv += __ldcg(&t_key[sidx]) != kEmptyVoxel;
+  for (int r = tid; r < t.npts; r += kThreads) ni += (__ldcg(&t_coord[B.slot[t.idx_off + r]]) >> 21) > height;
   int tot_v, tot_i;
-  block_excl_scan(nv, s_warp, tot_v);
-  block_excl_scan(ni, s_warp, tot_i);
+  block_excl_scan<kThreads>(nv, s_warp, tot_v);
+  block_excl_scan<kThreads>(ni, s_warp, tot_i);
   if (tid == 0) { B.ts[blockIdx.x].nvox = tot_v; B.ts[blockIdx.x].ninvis = tot_i; }
 }
 
@@ -630,7 +648,8 @@ __global__ void __launch_bounds__(kS1Threads) k_dcvc_rows(S1Buffers B, const int
   const int4 *events = B.events + t.idx_off;
   int2 *evc = B.evc + t.idx_off;
   uint16_t *rows = rows_all + (size_t)t.idx_off * 32;
-  for (int e0 = wid * 32; e0 < nev; e0 += kS1Threads) {
+  // grid (task, chunk of kS1Threads events): big tasks are spread over many CTAs
+  for (int e0 = blockIdx.y * kS1Threads + wid * 32; e0 < nev; e0 += gridDim.y * kS1Threads) {
     const int e = e0 + lane;
     int4 ev = make_int4(0, 0, 0, 0);
     if (e < nev) {
@@ -1209,7 +1228,8 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     S1_CUDA(cudaMemsetAsync(d_cur.p, 0, 8, st));
     trace("alloc + fills");
     k_s1_gather<<<nt, kS1Threads, 0, st>>>(B);
-    k_dcvc_prepare<<<nt, kS1Threads, 0, st>>>(B, 0.35, 0.0004, 1.2, 1.2, d_tab.p + 6 * n_tab);  // get_json.cpp:205-208
+    k_dcvc_prepare<kS1Threads><<<nt, kS1Threads, 0, st>>>(B, 0.35, 0.0004, 1.2, 1.2, d_tab.p + 6 * n_tab);
+    k_dcvc_prepare<1024><<<nt, 1024, 0, st>>>(B, 0.35, 0.0004, 1.2, 1.2, d_tab.p + 6 * n_tab);  // get_json.cpp:205-208
     trace("gather + prepare");
     {
       // table classes of the replay: every class is launched over all tasks, a CTA leaves at once unless its
@@ -1231,7 +1251,7 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
       static const int kCaps[3] = {2048, 8192, kCcMaxEv};
       if (use_cc) {
         S1_CUDA(cudaFuncSetAttribute(k_dcvc_replay_cc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc_smem(kCaps[2])));
-        k_dcvc_rows<<<nt, kS1Threads, 0, st>>>(B, d_tab.p + 6 * n_tab, sp.d_rows.p);
+        k_dcvc_rows<<<dim3(nt, 16), kS1Threads, 0, st>>>(B, d_tab.p + 6 * n_tab, sp.d_rows.p);
         S1_CUDA(cudaEventRecord(sp.ev[0], st));
         int nlo = -1;
         for (int c = 0; c < 3; ++c) {
