@@ -82,6 +82,7 @@ struct S1Buffers {
   int *t_key, *t_min1, *t_min2, *t_coord, *t_kind, *t_label;  // voxel table
   double *bounds;
   int *pool;         // (label, count, first) triples
+  int *pool_of_label; // per label value: index of its pool entry (labels that own points)
   unsigned long long *pool_cursor;
 };
 
@@ -1000,6 +1001,7 @@ __global__ void __launch_bounds__(kS1Threads) k_s1_finish(S1Buffers B) {
     if (c > 0) {
       int *o = B.pool + 3 * (s_pool + pos);
       o[0] = l; o[1] = c; o[2] = __ldcg(&first[l]);
+      B.pool_of_label[t.lab_off + l] = (int)(s_pool + pos);
       ++pos;
     }
   }
@@ -1008,71 +1010,108 @@ __global__ void __launch_bounds__(kS1Threads) k_s1_finish(S1Buffers B) {
 struct InstRec {  // one per instance, host-planned
   int task, label, inst_id, node_slot;  // node_slot: index into the node output or -1
   uint32_t node_label;
+  int pool_idx;                         // pool entry of the label (its centroid sits at that index)
 };
 
-// ---- K6: label -> instance id, per point membership ------------------------------------------
-__global__ void k_s1_scatter_map(S1Buffers B, const InstRec *inst, int ninst, int *inst_of_label, int *node_inst_of_label) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ninst) return;
-  const Task t = B.tasks[inst[i].task];
-  inst_of_label[t.lab_off + inst[i].label] = inst[i].inst_id;
-  if (inst[i].node_slot >= 0) node_inst_of_label[t.lab_off + inst[i].label] = i;  // index into inst[]
-}
-// membership of every point, and (key, position) pairs for the centroid pass: key = index of the point's
-// node instance (or all-ones), position = index of the point in the batch.  A stable sort by key then
-// lists every node instance's points contiguously in ascending point order.
-__global__ void __launch_bounds__(kS1Threads) k_s1_assign(S1Buffers B, const int *inst_of_label, const int *node_inst_of_label,
-                                                          int32_t *point_instance, uint32_t *skey, uint32_t *sval) {
+// The centroid of a node instance only depends on the label's points, not on the instance order the host
+// works out from the pool (unordered_map replay): K6a-K6c run on the GPU WHILE the host orders.
+// ---- K6a: per point (sort key, position): key = pool index of its label if the label will become a node
+//           instance (node class and large enough: get_json.cpp:146,228 / minSeg), else all-ones.
+__global__ void __launch_bounds__(kS1Threads) k_s1_lkey(S1Buffers B, uint32_t *skey, uint32_t *sval) {
   const Task t = B.tasks[blockIdx.x];
+  const bool node = t.cls >= 10 && t.cls <= 18;  // node_map(cls) in 3..11
+  const int *count = B.count + t.lab_off;
   for (int r = threadIdx.x; r < t.npts; r += kS1Threads) {
     const int lab = B.final_label[t.idx_off + r];
-    if (point_instance) {
-      const int id = inst_of_label[t.lab_off + lab];
-      if (id >= 0) point_instance[t.pt0 + B.cls_idx[t.idx_off + r]] = id;
+    uint32_t key = 0xFFFFFFFFu;
+    if (node) {
+      const int c = count[lab];
+      const bool ok = t.policy == P_DCVC ? c >= t.minSeg : (t.policy == P_GTINST ? c > 20 : true);
+      if (ok) key = (uint32_t)B.pool_of_label[t.lab_off + lab];
     }
-    skey[t.idx_off + r] = (uint32_t)node_inst_of_label[t.lab_off + lab];  // -1 -> 0xFFFFFFFF sorts last
+    skey[t.idx_off + r] = key;
     sval[t.idx_off + r] = (uint32_t)(t.pt0 + B.cls_idx[t.idx_off + r]);
   }
 }
 
-// ---- K7: centroid = sequential float32 sum in ascending point order (get_json.cpp:266-274) ----
-// One warp per node instance over ITS points only (contiguous in the instance-sorted position list):
-// 32 points are fetched per trip (coalesced list, gathered coordinates) and added in lane order, so the
-// rounding sequence is the reference's.
-__global__ void __launch_bounds__(128) k_s1_centroid(S1Buffers B, const InstRec *inst, int ninst, const uint32_t *sorted_pos,
-                                                     const int64_t *seg_off, sgtd_node *nodes) {
-  const int i = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+// ---- K6b (after a stable sort by key): centroid = sequential float32 sum in ascending point order
+// (get_json.cpp:266-274).  One warp per pool entry that owns sorted points (found by binary search):
+// 32 x kDepth points are fetched per trip (coalesced list, gathered coordinates) and added in lane order, so
+// the rounding sequence is the reference's.
+__global__ void __launch_bounds__(128) k_s1_lcentroid(S1Buffers B, const uint32_t *sorted_key, const uint32_t *sorted_pos,
+                                                      int64_t n_idx, float4 *cent) {
   const int lane = threadIdx.x & 31;
-  if (i >= ninst) return;
-  const InstRec ir = inst[i];
-  if (ir.node_slot < 0) return;
-  const int64_t s0 = seg_off[i], n = seg_off[i + 1] - s0;
-  float cx = 0.f, cy = 0.f, cz = 0.f;
-  constexpr int kDepth = 4;  // 128 points in flight per trip: the two dependent loads are issued for all of them first
-  for (int64_t j0 = 0; j0 < n; j0 += 32 * kDepth) {
-    float4 p[kDepth];
+  const long long npool = (long long)*B.pool_cursor;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < npool; i += nwarps) {
+    const int64_t n = B.pool[3 * i + 1];
+    int64_t lo = 0, hi = n_idx;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted_key[mid] < (uint32_t)i) lo = mid + 1; else hi = mid; }
+    if (lo >= n_idx || sorted_key[lo] != (uint32_t)i) continue;  // not a node instance
+    const int64_t s0 = lo;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    constexpr int kDepth = 4;  // 128 points per trip; the next trip's two dependent loads are in flight while this one is summed
+    float4 q[kDepth];
+    auto fetch = [&](int64_t j0) {
 #pragma unroll
-    for (int u = 0; u < kDepth; ++u) {
-      const int64_t j = j0 + 32 * u + lane;
-      p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < n) p[u] = B.pts[sorted_pos[s0 + j]];
-    }
+      for (int u = 0; u < kDepth; ++u) {
+        const int64_t j = j0 + 32 * u + lane;
+        q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < n) q[u] = B.pts[sorted_pos[s0 + j]];
+      }
+    };
+    fetch(0);
+    for (int64_t j0 = 0; j0 < n; j0 += 32 * kDepth) {
+      float4 p[kDepth];
 #pragma unroll
-    for (int u = 0; u < kDepth; ++u) {
-      const int m = (int)max((int64_t)0, min((int64_t)32, n - j0 - 32 * u));
-      for (int l = 0; l < m; ++l) {
-        cx = __fadd_rn(cx, __shfl_sync(0xffffffffu, p[u].x, l));
-        cy = __fadd_rn(cy, __shfl_sync(0xffffffffu, p[u].y, l));
-        cz = __fadd_rn(cz, __shfl_sync(0xffffffffu, p[u].z, l));
+      for (int u = 0; u < kDepth; ++u) p[u] = q[u];
+      if (j0 + 32 * kDepth < n) fetch(j0 + 32 * kDepth);
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u) {
+        const int m = (int)max((int64_t)0, min((int64_t)32, n - j0 - 32 * u));
+        if (m == 32) {
+          // full tile: unrolled, so that the broadcasts pipeline and only the three add chains are serial
+#pragma unroll
+          for (int l = 0; l < 32; ++l) {
+            cx = __fadd_rn(cx, __shfl_sync(0xffffffffu, p[u].x, l));
+            cy = __fadd_rn(cy, __shfl_sync(0xffffffffu, p[u].y, l));
+            cz = __fadd_rn(cz, __shfl_sync(0xffffffffu, p[u].z, l));
+          }
+        } else {
+          for (int l = 0; l < m; ++l) {
+            cx = __fadd_rn(cx, __shfl_sync(0xffffffffu, p[u].x, l));
+            cy = __fadd_rn(cy, __shfl_sync(0xffffffffu, p[u].y, l));
+            cz = __fadd_rn(cz, __shfl_sync(0xffffffffu, p[u].z, l));
+          }
+        }
       }
     }
+    if (lane == 0) {
+      const float cnt = (float)n;
+      cent[i] = make_float4(__fdiv_rn(cx, cnt), __fdiv_rn(cy, cnt), __fdiv_rn(cz, cnt), 0.f);
+    }
   }
-  if (lane == 0) {
-    const float cnt = (float)n;
+}
+
+// ---- K7 (after the host has ordered the instances): label -> instance id, node records, membership
+__global__ void k_s1_scatter_map(S1Buffers B, const InstRec *inst, int ninst, int *inst_of_label, const float4 *cent, sgtd_node *nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ninst) return;
+  const InstRec ir = inst[i];
+  const Task t = B.tasks[ir.task];
+  inst_of_label[t.lab_off + ir.label] = ir.inst_id;
+  if (ir.node_slot >= 0) {
+    const float4 c = cent[ir.pool_idx];
     sgtd_node nd;
-    nd.x = __fdiv_rn(cx, cnt); nd.y = __fdiv_rn(cy, cnt); nd.z = __fdiv_rn(cz, cnt);
-    nd.label = ir.node_label;
+    nd.x = c.x; nd.y = c.y; nd.z = c.z; nd.label = ir.node_label;
     nodes[ir.node_slot] = nd;
+  }
+}
+__global__ void __launch_bounds__(kS1Threads) k_s1_assign(S1Buffers B, const int *inst_of_label, int32_t *point_instance) {
+  const Task t = B.tasks[blockIdx.x];
+  for (int r = threadIdx.x; r < t.npts; r += kS1Threads) {
+    const int id = inst_of_label[t.lab_off + B.final_label[t.idx_off + r]];
+    if (id >= 0) point_instance[t.pt0 + B.cls_idx[t.idx_off + r]] = id;
   }
 }
 
@@ -1094,14 +1133,14 @@ struct S1Pool {
   DevBuf<int> d_pp, d_tab, d_lab, d_pool, d_map; DevBuf<double> d_polar, d_bounds; DevBuf<unsigned long long> d_cur;
   DevBuf<InstRec> d_inst; DevBuf<sgtd_node> d_nodes;
   DevBuf<uint16_t> d_rows; DevBuf<int> d_map2; DevBuf<uint32_t> d_sort; DevBuf<int64_t> d_seg; DevBuf<unsigned char> d_cub;
-  DevBuf<float4> in_pts; DevBuf<uint32_t> in_lab; DevBuf<int32_t> out_pi;  // staging of host inputs / outputs
+  DevBuf<float4> d_cent; DevBuf<float4> in_pts; DevBuf<uint32_t> in_lab; DevBuf<int32_t> out_pi;  // staging of host inputs / outputs
   cudaStream_t side[4] = {}; cudaEvent_t ev[5] = {}; bool have_streams = false;  // concurrent replay classes
   ~S1Pool() {
     if (have_streams) { for (auto x : side) cudaStreamDestroy(x); for (auto x : ev) cudaEventDestroy(x); }
     d_off.release(); d_cnt.release(); d_tasks.release(); d_ts.release(); d_pp.release(); d_tab.release(); d_lab.release();
     d_pool.release(); d_map.release(); d_polar.release(); d_bounds.release(); d_cur.release(); d_inst.release();
     d_nodes.release(); in_pts.release(); in_lab.release(); out_pi.release();
-    d_rows.release(); d_map2.release(); d_sort.release(); d_seg.release(); d_cub.release();
+    d_cent.release(); d_rows.release(); d_map2.release(); d_sort.release(); d_seg.release(); d_cub.release();
   }
 };
 static void s1_pool_free(void *p) { delete static_cast<S1Pool *>(p); }
@@ -1147,7 +1186,6 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
   std::vector<TaskState> ts;
   std::vector<int> pool;
   std::vector<InstRec> inst;
-  std::vector<int64_t> seg;  // per instance: start of its points in the instance-sorted position list
   int64_t n_idx = 0, n_tab = 0, n_lab = 0, n_bnd = 0;
   S1Buffers B{};
   unsigned long long cursor = 0;
@@ -1207,6 +1245,9 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     S1_CUDA(d_pool.reserve((size_t)std::max<int64_t>(n_lab, 1) * 3, st, false));
     S1_CUDA(d_cur.reserve(1, st, false));
     S1_CUDA(d_map.reserve((size_t)std::max<int64_t>(n_lab, 1), st, false));
+    S1_CUDA(d_map2.reserve((size_t)std::max<int64_t>(n_lab, 1), st, false));  // pool entry of each label
+    S1_CUDA(d_sort.reserve((size_t)std::max<int64_t>(n_idx, 1) * 4, st, false));  // key / value double buffers
+    S1_CUDA(sp.d_cent.reserve((size_t)std::max<int64_t>(n_lab, 1), st, false));  // centroid per pool entry (sparsely touched)
     B.pts = d_pts; B.labels = d_labels; B.tasks = d_tasks.p; B.ts = d_ts.p;
     B.cls_idx = d_pp.p; B.slot = d_pp.p + n_idx; B.pt_label = d_pp.p + 2 * n_idx; B.final_label = d_pp.p + 3 * n_idx;
     B.events = reinterpret_cast<int4 *>(d_pp.p + 4 * n_idx);  // 4*n_idx ints = 16-byte aligned
@@ -1215,7 +1256,7 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     B.t_key = d_tab.p; B.t_min1 = d_tab.p + n_tab; B.t_min2 = d_tab.p + 2 * n_tab; B.t_coord = d_tab.p + 3 * n_tab;
     B.t_kind = d_tab.p + 4 * n_tab; B.t_label = d_tab.p + 5 * n_tab;
     B.parent = d_lab.p; B.count = d_lab.p + n_lab; B.first = d_lab.p + 2 * n_lab;
-    B.bounds = d_bounds.p; B.pool = d_pool.p; B.pool_cursor = d_cur.p;
+    B.bounds = d_bounds.p; B.pool = d_pool.p; B.pool_cursor = d_cur.p; B.pool_of_label = d_map2.p;
     // initial values: keys empty, min1/min2/first = INT_MAX, kind/label/count = 0/-1/0, maps -1
     k_fill_i32<<<1024, 256, 0, st>>>(B.t_key, 3 * n_tab, kEmptyVoxel);  // key, min1, min2
     k_fill_i32<<<1024, 256, 0, st>>>(B.t_kind, n_tab, K_NONE);
@@ -1279,12 +1320,33 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     k_s1_finish<<<nt, kS1Threads, 0, st>>>(B);
     h->launches += 16;
     S1_CUDA(cudaGetLastError());
-    S1_CUDA(cudaMemcpyAsync(ts.data(), d_ts.p, nt * sizeof(TaskState), cudaMemcpyDeviceToHost, st));
-    S1_CUDA(cudaMemcpyAsync(&cursor, d_cur.p, 8, cudaMemcpyDeviceToHost, st));
-    S1_CUDA(cudaStreamSynchronize(st));
+    // The label pool goes to the host on a side stream; meanwhile the main stream lists every would-be node
+    // instance's points (stable sort by pool index) and sums their centroids -- neither depends on the
+    // instance ORDER the host is about to work out.
+    S1_CUDA(cudaEventRecord(sp.ev[0], st));
+    cudaStream_t sd = sp.side[0];
+    S1_CUDA(cudaStreamWaitEvent(sd, sp.ev[0], 0));
+    S1_CUDA(cudaMemcpyAsync(ts.data(), d_ts.p, nt * sizeof(TaskState), cudaMemcpyDeviceToHost, sd));
+    S1_CUDA(cudaMemcpyAsync(&cursor, d_cur.p, 8, cudaMemcpyDeviceToHost, sd));
+    uint32_t *k0 = d_sort.p, *k1 = d_sort.p + n_idx, *v0 = d_sort.p + 2 * n_idx, *v1 = d_sort.p + 3 * n_idx;
+    {
+      k_s1_lkey<<<nt, kS1Threads, 0, st>>>(B, k0, v0);
+      int bits = 1;  // pool indices are below the number of label slots
+      while ((1ll << bits) <= n_lab) ++bits;
+      size_t cb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, cb, k0, k1, v0, v1, (int)n_idx, 0, bits, st);
+      S1_CUDA(d_cub.reserve(cb, st, false));
+      // (all-ones keys -- points outside node instances -- are the largest value in the low `bits` bits too:
+      // they end up behind every pool index)
+      S1_CUDA(cub::DeviceRadixSort::SortPairs(d_cub.p, cb, k0, k1, v0, v1, (int)n_idx, 0, std::min(32, (bits + 7) / 8 * 8), st));
+      k_s1_lcentroid<<<h->sm_count * 32, 128, 0, st>>>(B, k1, v1, n_idx, sp.d_cent.p);
+      h->launches += 3;
+      S1_CUDA(cudaGetLastError());
+    }
+    S1_CUDA(cudaStreamSynchronize(sd));
     pool.resize((size_t)cursor * 3 + 3);
-    if (cursor) S1_CUDA(cudaMemcpyAsync(pool.data(), d_pool.p, (size_t)cursor * 12, cudaMemcpyDeviceToHost, st));
-    S1_CUDA(cudaStreamSynchronize(st));
+    if (cursor) S1_CUDA(cudaMemcpyAsync(pool.data(), d_pool.p, (size_t)cursor * 12, cudaMemcpyDeviceToHost, sd));
+    S1_CUDA(cudaStreamSynchronize(sd));
     trace("finish + D2H labels");
     if (h->opt.s1_trace) {
       std::vector<int> ord(nt);
@@ -1303,14 +1365,14 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     // in ascending point order.  That order only depends on the key sequence, so the real container is
     // replayed with the labels in first-appearance order (mapped type irrelevant).  Tasks are independent:
     // they are ordered on a few host threads.
-    struct L { int label, count, first; };
+    struct L { int label, count, first, pidx; };
     std::vector<std::vector<L>> orders((size_t)nt);
     auto order_task = [&](int ti) {
       const Task &t = tasks[ti];
       std::vector<L> ls((size_t)ts[ti].ndistinct);
       for (int j = 0; j < ts[ti].ndistinct; ++j) {
         const int *p = &pool[(size_t)(ts[ti].pool_off + j) * 3];
-        ls[j] = L{p[0], p[1], p[2]};
+        ls[j] = L{p[0], p[1], p[2], (int)(ts[ti].pool_off + j)};
       }
       std::vector<L> &order = orders[(size_t)ti];
       if (t.policy == P_DCVC) {
@@ -1339,7 +1401,7 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
       }
     }
     int cur_scan = -1, inst_id = 0;
-    int64_t node_cursor = 0, seg_cursor = 0;
+    int64_t node_cursor = 0;
     for (int ti = 0; ti < nt; ++ti) {
       const Task &t = tasks[ti];
       if (t.scan != cur_scan) {
@@ -1353,11 +1415,9 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
         InstRec ir{};
         ir.task = ti; ir.label = l.label; ir.inst_id = inst_id++;
         ir.node_slot = -1; ir.node_label = 0;
+        ir.pool_idx = l.pidx;
         if (mapped >= 3 && mapped <= 12) { ir.node_slot = (int)node_cursor++; ir.node_label = (uint32_t)mapped; }
         inst.push_back(ir);
-        // node instances are sorted by their index in inst[]: their point lists follow each other
-        seg.push_back(seg_cursor);
-        if (ir.node_slot >= 0) seg_cursor += l.count;
       }
     }
     if (cur_scan >= 0) n_instances[cur_scan] = inst_id;
@@ -1366,34 +1426,16 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
     trace("instance order (host)");
     if (!inst.empty()) {
       const int ni = (int)inst.size();
-      seg.push_back(seg_cursor);
       S1_CUDA(d_inst.reserve(ni, st, false));
       S1_CUDA(cudaMemcpyAsync(d_inst.p, inst.data(), ni * sizeof(InstRec), cudaMemcpyHostToDevice, st));
-      S1_CUDA(d_seg.reserve((size_t)ni + 1, st, false));
-      S1_CUDA(cudaMemcpyAsync(d_seg.p, seg.data(), ((size_t)ni + 1) * 8, cudaMemcpyHostToDevice, st));
       S1_CUDA(d_nodes.reserve((size_t)std::max<int64_t>(node_cursor, 1), st, false));
-      S1_CUDA(d_map2.reserve((size_t)std::max<int64_t>(n_lab, 1), st, false));
-      S1_CUDA(d_sort.reserve((size_t)std::max<int64_t>(n_idx, 1) * 4, st, false));  // key / value double buffers
-      k_fill_i32<<<1024, 256, 0, st>>>(d_map2.p, n_lab, -1);
-      k_s1_scatter_map<<<(ni + 255) / 256, 256, 0, st>>>(B, d_inst.p, ni, d_map.p, d_map2.p);
-      uint32_t *k0 = d_sort.p, *k1 = d_sort.p + n_idx, *v0 = d_sort.p + 2 * n_idx, *v1 = d_sort.p + 3 * n_idx;
-      k_s1_assign<<<nt, kS1Threads, 0, st>>>(B, d_map.p, d_map2.p, d_point_instance, k0, v0);
-      {
-        // stable LSD radix sort on the bits an instance index needs; all-ones keys (points outside node
-        // instances) end up behind every instance
-        int bits = 1;
-        while ((1ll << bits) <= ni) ++bits;
-        size_t cb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, cb, k0, k1, v0, v1, (int)n_idx, 0, bits, st);
-        S1_CUDA(d_cub.reserve(cb, st, false));
-        S1_CUDA(cub::DeviceRadixSort::SortPairs(d_cub.p, cb, k0, k1, v0, v1, (int)n_idx, 0, bits, st));
-      }
-      k_s1_centroid<<<(ni + 3) / 4, 128, 0, st>>>(B, d_inst.p, ni, v1, d_seg.p, d_nodes.p);
-      h->launches += 5;
+      k_s1_scatter_map<<<(ni + 255) / 256, 256, 0, st>>>(B, d_inst.p, ni, d_map.p, sp.d_cent.p, d_nodes.p);
+      if (d_point_instance) k_s1_assign<<<nt, kS1Threads, 0, st>>>(B, d_map.p, d_point_instance);
+      h->launches += 2;
       S1_CUDA(cudaGetLastError());
       if (node_cursor) S1_CUDA(cudaMemcpyAsync(nodes_out.data(), d_nodes.p, (size_t)node_cursor * sizeof(sgtd_node), cudaMemcpyDeviceToHost, st));
-      S1_CUDA(cudaStreamSynchronize(st));
     }
+    S1_CUDA(cudaStreamSynchronize(st));
     trace("assign + centroid + D2H");
   }
   (void)total_pts;
