@@ -551,6 +551,15 @@ def run_ours(args):
         vote_ms.append(tm["vote_ms"]); stats = st
         for kk, vv in tm.items():
             stage[kk] = stage.get(kk, 0.0) + vv / len(kept)
+    # shards differ (database density, where the batch's candidates fall): slowest / fastest rank per stage
+    stage_spread = None
+    if world > 1:
+        keys = [kk for kk in ("probe_ms", "vote_ms", "topk_ms", "exchange_ms", "collect_ms", "verify_ms", "total_ms") if kk in stage]
+        tmax = torch.tensor([stage[kk] for kk in keys], device=dev, dtype=torch.float64)
+        tmin = tmax.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        stage_spread = {kk: [round(float(a), 3), round(float(b), 3)] for kk, a, b in zip(keys, tmin.tolist(), tmax.tolist())}
     ms_e2e, kept = timer(step_e2e, args.steps)
     loops = np.frombuffer(loops_pin.numpy().tobytes(), capi.LOOP_DTYPE)
     cands_h = np.frombuffer(cands_pin.numpy().tobytes(), capi.CAND_DTYPE).reshape(nq, k)
@@ -595,6 +604,7 @@ def run_ours(args):
             "parity_checked": parity,
             "roofline": roof,
             "stage_ms": {kk: round(vv, 3) for kk, vv in stage.items()},
+            "stage_ms_min_max_over_ranks": stage_spread,
             "recall": success_stats(loops, cands_h, cfg["world"]["poses"], cfg["qposes"]),
             # checksum of (best frame, score, candidate frames/votes/scores): identical for every N
             "result_crc": result_crc(loops, cands_h.reshape(-1)),

@@ -31,10 +31,14 @@ bool is_device_ptr(const void *p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-__global__ void k_pack_descs(const sgtd_desc *in, int64_t n, DescRec *rec, DescVert *vert) {
+// bad (optional): set when a side length cannot be turned into a key (negative, NaN, or >= 60000 cells:
+// pack_key keeps 16 bits per side)
+__global__ void k_pack_descs(const sgtd_desc *in, int64_t n, DescRec *rec, DescVert *vert, int *bad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const sgtd_desc d = in[i];
+  if (bad && !(d.side[0] >= 0.0 && d.side[0] < 60000.0 && d.side[1] >= 0.0 && d.side[1] < 60000.0 && d.side[2] >= 0.0 && d.side[2] < 60000.0))
+    *bad = 1;
   DescRec r;
   r.s[0] = d.side[0]; r.s[1] = d.side[1]; r.s[2] = d.side[2];
   r.frame = d.frame;
@@ -310,6 +314,12 @@ int sgtd_build_descriptors(sgtd_handle *h, const sgtd_node *nodes, const int64_t
 int sgtd_desc_batch_upload(sgtd_handle *h, const sgtd_desc *descs, const int64_t *scan_offsets, int32_t nscans,
                            sgtd_desc_batch **out) {
   if (!h || !out || nscans < 0 || (nscans > 0 && !scan_offsets)) SGTD_FAIL(h, SGTD_E_INVALID, "bad argument");
+  if (nscans > 0) {
+    if (scan_offsets[0] != 0) SGTD_FAIL(h, SGTD_E_INVALID, "scan_offsets[0] must be 0");
+    for (int32_t i = 0; i < nscans; ++i)
+      if (scan_offsets[i] > scan_offsets[i + 1]) SGTD_FAIL(h, SGTD_E_INVALID, "scan_offsets must not decrease");
+    if (scan_offsets[nscans] > 0 && !descs) SGTD_FAIL(h, SGTD_E_INVALID, "descs is NULL");
+  }
   SetDevice sd(h->device);
   cudaStream_t st = h->stream;
   sgtd_desc_batch *b = take_batch(h);
@@ -332,11 +342,17 @@ int sgtd_desc_batch_upload(sgtd_handle *h, const sgtd_desc *descs, const int64_t
       if ((e = cudaMemcpyAsync(staged.p, descs, (size_t)b->n * sizeof(sgtd_desc), cudaMemcpyHostToDevice, st)) != cudaSuccess) { staged.release(); return bail(e, "copy descs"); }
       src = staged.p;
     }
-    k_pack_descs<<<(unsigned)((b->n + 255) / 256), 256, 0, st>>>(src, b->n, b->rec.p, b->vert.p);
+    DevBuf<int> d_bad;
+    int bad = 0;
+    if ((e = d_bad.reserve(1, st, false)) != cudaSuccess) { staged.release(); return bail(e, "alloc flag"); }
+    cudaMemsetAsync(d_bad.p, 0, sizeof(int), st);
+    k_pack_descs<<<(unsigned)((b->n + 255) / 256), 256, 0, st>>>(src, b->n, b->rec.p, b->vert.p, d_bad.p);
     SGTD_LAUNCHED(h);
-    e = cudaStreamSynchronize(st);
-    staged.release();
+    e = cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    staged.release(); d_bad.release();
     if (e != cudaSuccess) return bail(e, "k_pack_descs");
+    if (bad) { sgtd_desc_batch_free(b); SGTD_FAIL(h, SGTD_E_INVALID, "descriptor side length outside [0, 60000)"); }
   } else {
     cudaStreamSynchronize(st);
   }
@@ -477,6 +493,7 @@ static int fetch_cand(sgtd_handle *h, const sgtd_search_result *r, int32_t q, in
 int sgtd_result_matches(sgtd_handle *h, const sgtd_search_result *r, int32_t q, int32_t c, int32_t *m_q, uint8_t *m_cell,
                         uint32_t *m_g, int64_t cap) {
   sgtd_candidate cd;
+  if (!h || !r) return sgtd_fail(h, SGTD_E_INVALID, "bad argument", __FILE__, __LINE__);
   SetDevice sd(h->device);
   int rc = fetch_cand(h, r, q, c, &cd);
   if (rc) return rc;
@@ -491,6 +508,7 @@ int sgtd_result_matches(sgtd_handle *h, const sgtd_search_result *r, int32_t q, 
 
 int sgtd_result_inliers(sgtd_handle *h, const sgtd_search_result *r, int32_t q, int32_t c, int32_t *inl, int64_t cap) {
   sgtd_candidate cd;
+  if (!h || !r) return sgtd_fail(h, SGTD_E_INVALID, "bad argument", __FILE__, __LINE__);
   SetDevice sd(h->device);
   int rc = fetch_cand(h, r, q, c, &cd);
   if (rc) return rc;
@@ -534,6 +552,8 @@ int sgtd_result_free(sgtd_search_result *r) {
 int sgtd_db_fetch(sgtd_handle *h, const uint32_t *g, int64_t n, sgtd_desc *out) {
   if (!h || !g || !out || n < 0) SGTD_FAIL(h, SGTD_E_INVALID, "bad argument");
   if (n == 0) return SGTD_OK;
+  for (int64_t i = 0; i < n; ++i)
+    if ((size_t)g[i] >= h->rec.n) SGTD_FAIL(h, SGTD_E_INVALID, "descriptor index out of range");
   SetDevice sd(h->device);
   DevBuf<uint32_t> dg; DevBuf<sgtd_desc> dd;
   SGTD_CUDA(h, dg.reserve((size_t)n, h->stream, false));
@@ -612,21 +632,56 @@ int sgtd_db_load(sgtd_handle *h, const char *path) {
     fclose(f);
     SGTD_FAIL(h, SGTD_E_INVALID, "snapshot was made with a different std_side_resolution or shard layout");
   }
-  std::vector<int64_t> foff((size_t)hd.n_frames + 1);
+  // the header is not trusted: sizes against the file, then the offset table
+  long fsize = 0;
+  if (fseek(f, 0, SEEK_END) == 0) fsize = ftell(f);
+  const unsigned long long need = sizeof(hd) + ((unsigned long long)hd.n_frames + 1) * 8ull +
+                                  (unsigned long long)hd.n_desc * (sizeof(DescRec) + sizeof(DescVert));
+  if (fsize < 0 || (unsigned long long)fsize < need || hd.n_desc >= (1ll << 32) || hd.n_frames >= (1ll << 31) ||
+      fseek(f, (long)sizeof(hd), SEEK_SET) != 0) {
+    fclose(f);
+    SGTD_FAIL(h, SGTD_E_IO, "snapshot header does not match the file size");
+  }
+  std::vector<int64_t> foff;
+  std::vector<unsigned char> host;
+  const size_t chunk = 1u << 20;
+  try {
+    foff.resize((size_t)hd.n_frames + 1);
+    host.resize(chunk * sizeof(DescVert));
+  } catch (const std::exception &) {
+    fclose(f);
+    SGTD_FAIL(h, SGTD_E_IO, "out of host memory while loading the snapshot");
+  }
   bool ok = fread(foff.data(), 8, foff.size(), f) == foff.size();
+  if (ok) {
+    bool good = foff[0] == 0 && foff[(size_t)hd.n_frames] == hd.n_desc;
+    for (size_t i = 0; good && i < (size_t)hd.n_frames; ++i) good = foff[i] <= foff[i + 1];
+    if (!good) {
+      fclose(f);
+      SGTD_FAIL(h, SGTD_E_IO, "corrupt snapshot: frame offsets");
+    }
+  }
   cudaError_t e = cudaSuccess;
   if (ok) {
     e = h->rec.reserve((size_t)std::max<int64_t>(hd.n_desc, 1), h->stream, false);
     if (e == cudaSuccess) e = h->vert.reserve((size_t)std::max<int64_t>(hd.n_desc, 1), h->stream, false);
   }
-  const size_t chunk = 1u << 20;
-  std::vector<unsigned char> host(chunk * sizeof(DescVert));
+  bool frames_ok = true;
   for (int pass = 0; pass < 2 && ok && e == cudaSuccess; ++pass) {
     const size_t esz = pass ? sizeof(DescVert) : sizeof(DescRec);
     unsigned char *dst = pass ? (unsigned char *)h->vert.p : (unsigned char *)h->rec.p;
     for (size_t i = 0; i < (size_t)hd.n_desc && ok && e == cudaSuccess; i += chunk) {
       const size_t n = std::min(chunk, (size_t)hd.n_desc - i);
       ok = fread(host.data(), esz, n, f) == n;
+      if (ok && pass == 0) {
+        // every record must sit in the keyframe its position says (vote rows and views are indexed by it)
+        const DescRec *rr = reinterpret_cast<const DescRec *>(host.data());
+        size_t fr = (size_t)(std::upper_bound(foff.begin(), foff.end(), (int64_t)i) - foff.begin()) - 1;
+        for (size_t j = 0; j < n && frames_ok; ++j) {
+          while (fr + 1 < foff.size() && (int64_t)(i + j) >= foff[fr + 1]) ++fr;
+          frames_ok = (int64_t)rr[j].frame == hd.frame_lo + (int64_t)fr && rr[j].code < 4096;
+        }
+      }
       if (ok) {
         e = cudaMemcpyAsync(dst + i * esz, host.data(), n * esz, cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -636,6 +691,7 @@ int sgtd_db_load(sgtd_handle *h, const char *path) {
   fclose(f);
   if (e != cudaSuccess) return sgtd_fail(h, SGTD_E_CUDA, "snapshot H2D", __FILE__, __LINE__, e);
   if (!ok) SGTD_FAIL(h, SGTD_E_IO, "truncated snapshot");
+  if (!frames_ok) SGTD_FAIL(h, SGTD_E_IO, "corrupt snapshot: descriptor records outside their keyframe");
   h->rec.n = h->vert.n = (size_t)hd.n_desc;
   h->frame_off = foff;
   h->current_frame_id = hd.current_frame_id;

@@ -267,9 +267,44 @@ def test_db_snapshot_roundtrip(world, built, tmp_path):
     m3 = capi.STDescManager(device=0, std_side_resolution=0.5)
     with pytest.raises(capi.SgtdError):
         m3.load(path)                                   # keys depend on the side scaling
-    open(path, "r+b").truncate(1000)
+    # a snapshot is not trusted: corrupt frame offsets, records outside their keyframe, a header that
+    # promises more than the file holds and a truncated file are all refused (no crash, no bad_alloc)
+    import struct
+    raw = open(path, "rb").read()
+    n_desc, n_frames = struct.unpack_from("<qq", raw, 16)
+    assert n_desc == mgr.db_size and n_frames == mgr.current_frame_id_
+    hdr = len(raw) - (n_frames + 1) * 8 - n_desc * 80    # header, frame offsets, 32 + 48 bytes per descriptor
+    rec0 = hdr + (n_frames + 1) * 8
+    patches = {
+        "offsets": lambda b: b[:hdr + 8] + struct.pack("<q", 10 ** 12) + b[hdr + 16:],
+        "record_frame": lambda b: b[:rec0 + 24] + struct.pack("<I", 7) + b[rec0 + 28:],   # DescRec.frame of record 0
+        "huge_header": lambda b: b[:16] + struct.pack("<q", 1 << 40) + b[24:],
+        "truncated": lambda b: b[:1000],
+    }
+    for name, patch in patches.items():
+        bad = str(tmp_path / ("bad_" + name + ".sgtd"))
+        open(bad, "wb").write(patch(raw))
+        with pytest.raises(capi.SgtdError):
+            capi.STDescManager(device=0).load(bad)
+
+
+def test_boundary_rejects_bad_arguments(world, built):
+    """Out-of-range descriptor indices, malformed upload offsets and side lengths that cannot be keyed are
+    reported as SGTD_E_INVALID instead of being read or wrapped."""
+    mgr, o, gdesc, goff, _ = built
     with pytest.raises(capi.SgtdError):
-        capi.STDescManager(device=0).load(path)
+        mgr.db_fetch(np.array([mgr.db_size], dtype=np.uint32))
+    d = gdesc[:4].copy()
+    with pytest.raises(capi.SgtdError):
+        mgr.upload(d, np.array([1, 4], dtype=np.int64))
+    with pytest.raises(capi.SgtdError):
+        mgr.upload(d, np.array([0, 3, 2, 4], dtype=np.int64))
+    d["side"][2, 1] = 70000.0
+    with pytest.raises(capi.SgtdError):
+        mgr.upload(d, np.array([0, 4], dtype=np.int64))
+    d["side"][2, 1] = np.nan
+    with pytest.raises(capi.SgtdError):
+        mgr.upload(d, np.array([0, 4], dtype=np.int64))
 
 
 def test_single_scan_facade_flow(world, oracle_lib):
