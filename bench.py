@@ -74,6 +74,9 @@ def parse():
     ap.add_argument("--workload", default="city", choices=["city", "seq"],
                     help="city: configs[3] node-level DB (default, the metric's config); "
                          "seq: configs[1]-shaped labelled-scan sequence, stages 1-4 per query scan")
+    ap.add_argument("--shards", type=int, default=0,
+                    help="city, N > 1: keyframe-range shards S (default 0 = N: one shard per GPU, the metric's layout). "
+                         "S < N: N / S replicas of every shard, each group of S ranks serves its own slice of the query batch")
     ap.add_argument("--scans", type=int, default=1024, help="seq: map keyframes (scans)")
     ap.add_argument("--batch", type=int, default=128, help="seq: query scans per call")
     return ap.parse_args()
@@ -466,12 +469,27 @@ def run_ours(args):
     nq = qo.shape[0] - 1
 
     mgr = capi.STDescManager(device=local)
-    fpr = (nkf + world - 1) // world
-    if world > 1:
-        uid = torch.from_numpy(capi.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
-        dist.broadcast(uid, 0)
-        mgr.shard_init(rank, world, fpr, uid.cpu().numpy())
-    lo, hi = (rank * fpr, min(nkf, (rank + 1) * fpr)) if world > 1 else (0, nkf)
+    # layout: S keyframe-range shards x R = N / S replicas; replica group g (ranks g*S .. g*S+S-1) serves
+    # queries [g*nq/R, (g+1)*nq/R) against its own copy of the S shards.  Default S = N (R = 1): every GPU
+    # holds one shard and votes the whole batch (BASELINE.json configs[3]).
+    S = args.shards if args.shards > 0 else world
+    assert world % S == 0, "--shards must divide the number of GPUs"
+    R = world // S
+    grp, srank = rank // S, rank % S
+    fpr = (nkf + S - 1) // S
+    if S > 1:
+        mine = torch.from_numpy(capi.nccl_unique_id()).to(dev)
+        ids = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(ids, mine)                 # the id of a group is its leader's
+        mgr.shard_init(srank, S, fpr, ids[grp * S].cpu().numpy())
+    lo, hi = (srank * fpr, min(nkf, (srank + 1) * fpr)) if S > 1 else (0, nkf)
+    if R > 1:
+        q0, q1 = grp * nq // R, (grp + 1) * nq // R
+        qx, ql = qx[qo[q0]:qo[q1]], ql[qo[q0]:qo[q1]]
+        qo = (qo[q0:q1 + 1] - qo[q0]).astype(np.int64)
+        nq_all, nq = nq, q1 - q0
+    else:
+        q0, nq_all = 0, nq
 
     # ---- database build (not timed): stage 2 on the GPU for this rank's keyframes ----
     t0 = time.time()
@@ -563,6 +581,17 @@ def run_ours(args):
     ms_e2e, kept = timer(step_e2e, args.steps)
     loops = np.frombuffer(loops_pin.numpy().tobytes(), capi.LOOP_DTYPE)
     cands_h = np.frombuffer(cands_pin.numpy().tobytes(), capi.CAND_DTYPE).reshape(nq, k)
+    if R > 1:
+        # the replica groups' slices of the batch, in query order, for the checksum and the success statistics
+        # (every rank of a group holds the group's results; equal slice sizes are required here)
+        assert nq_all % R == 0, "--shards: the query batch must split evenly over the replica groups"
+        def gather(a):
+            t = torch.from_numpy(np.frombuffer(a.tobytes(), np.uint8).copy()).to(dev)
+            parts = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            return np.concatenate([parts[g * S].cpu().numpy() for g in range(R)])
+        loops = np.frombuffer(gather(loops).tobytes(), capi.LOOP_DTYPE)
+        cands_h = np.frombuffer(gather(cands_h).tobytes(), capi.CAND_DTYPE).reshape(nq_all, k)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -591,15 +620,16 @@ def run_ours(args):
         else:
             roof.update({"achieved": None, "frac": None})
         line = {
-            "metric": METRIC, "value": nq * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
+            "metric": METRIC, "value": nq_all * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "keyframes": nkf, "queries": nq, "db_descriptors": None,
-                       "sharding": f"keyframe-range x{world}", "l2": "inputs larger than L2 (DB index >> 126 MB)"},
+            "config": {"workload": WORKLOAD, "keyframes": nkf, "queries": nq_all, "db_descriptors": None,
+                       "sharding": f"keyframe-range x{S}" + (f", {R} replicas of every shard, one slice of the batch per replica group" if R > 1 else ""),
+                       "l2": "inputs larger than L2 (DB index >> 126 MB)"},
             "db_build_s": round(t_db, 2),
-            "e2e": {"value": nq * args.steps / (ms_e2e * 1e-3), "unit": "queries/s",
-                    "h2d_bytes_per_step": int(qnodes.nbytes + qo.nbytes),
-                    "d2h_bytes_per_step": int(loops_pin.numel() + cands_pin.numel())},
+            "e2e": {"value": nq_all * args.steps / (ms_e2e * 1e-3), "unit": "queries/s",
+                    "h2d_bytes_per_step": int(qnodes.nbytes + qo.nbytes) * R,
+                    "d2h_bytes_per_step": int(loops_pin.numel() + cands_pin.numel()) * R},
             "gpu_launches": int(launches),
             "parity_checked": parity,
             "roofline": roof,
@@ -614,7 +644,7 @@ def run_ours(args):
     if world > 1:
         t = torch.tensor([db_total], device=dev, dtype=torch.int64)
         dist.all_reduce(t)
-        db_total = int(t.item())
+        db_total = int(t.item()) // R              # every replica group holds the whole database once
         dist.barrier()
     mgr.close()
     del mgr

@@ -1381,8 +1381,8 @@ constexpr int kInvUnroll = 4;  // keyframe entries a thread looks up at a time (
 
 // dynamic shared memory: records [kSortCap] u32, sorted records [kSortCap] u32, per-descriptor
 // counters / offsets [bins] u16 (updated two per 32-bit atomic)
-template <int kHitUnroll>
-__global__ void __launch_bounds__(kCollectThreads, kHitUnroll >= 4 ? 2 : (kHitUnroll == 2 ? 3 : 4)) k_collect_inv(CollectInvParams P) {
+template <int kHitUnroll, int kMinBlocks>
+__global__ void __launch_bounds__(kCollectThreads, kMinBlocks) k_collect_inv(CollectInvParams P) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   uint32_t *s_rec = reinterpret_cast<uint32_t *>(s_dyn);
   uint32_t *s_out = s_rec + kSortCap;
@@ -2224,21 +2224,23 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
       I.m_q = r->m_q.p; I.m_g = r->m_g.p; I.m_cell = r->m_cell.p;
       // shared memory of a candidate CTA: two record arrays + one 16-bit counter per query descriptor
       const size_t inv_smem = 2 * (size_t)kSortCap * 4 + 4 * (size_t)((std::min<int64_t>(max_dq, kInvMaxDesc) + 1) / 2);
-      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        2 * kSortCap * 4 + 2 * kInvMaxDesc));
-      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        2 * kSortCap * 4 + 2 * kInvMaxDesc));
-      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        2 * kSortCap * 4 + 2 * kInvMaxDesc));
+      const int inv_smem_max = 2 * kSortCap * 4 + 2 * kInvMaxDesc;
+      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem_max));
+      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem_max));
+      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem_max));
+      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem_max));
+      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem_max));
       for (int qb0 = 0; qb0 < nq; qb0 += qt_group) {
         const int gq = std::min(qt_group, nq - qb0);
         k_query_index<<<gq, kIndexThreads, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (uint32_t *)(S + o_qtk), qt_ts,
                                                     (const uint32_t *)(S + o_qpr), r->cands.p, k);
         I.q_base = qb0;
         // (measured on the bench workload: 1 hit per thread and trip 5.0 ms, 2: 5.6, 4: 7.2 -- occupancy wins)
-        if (h->opt.collect_unroll == 4) k_collect_inv<4><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
-        else if (h->opt.collect_unroll == 2) k_collect_inv<2><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
-        else k_collect_inv<1><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
+        if (h->opt.collect_unroll == 4) k_collect_inv<4, 2><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
+        else if (h->opt.collect_unroll == 2) k_collect_inv<2, 3><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
+        else if (h->opt.collect_unroll == 5) k_collect_inv<1, 5><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
+        else if (h->opt.collect_unroll == 6) k_collect_inv<1, 6><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
+        else k_collect_inv<1, 4><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
         h->launches += 2;
       }
     }
