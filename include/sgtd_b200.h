@@ -171,7 +171,10 @@ int64_t sgtd_kernel_launches(const sgtd_handle *h);   /* kernels launched so far
  * kernel formulation runs: "vote_stream" (1 = the per-probe streaming vote kernel, exact FP64 on every
  * entry, instead of the bucket-major join), "join_groups" (query groups of the join, 0 = automatic),
  * "collect_mode" (0 auto, 1 inverted, 2 per-descriptor), "collect_group", "debug_novote",
- * "join_impl" (1 default; 0 / 2 experimental joins on 8-byte entries), "stats_unique", "s1_trace";
+ * "join_impl" (1 default; 0 / 2 experimental joins on 8-byte entries), "join_parts" (2..4: keyframe-range
+ * passes inside a query group), "join_hint" (vote REDs with an L2 evict-last policy), "collect_unroll",
+ * "verify_impl", "stats_unique", "s1_trace", "s1_replay" (1 = sequential stage-1 replay forms only; default 0 =
+ * component-parallel replay), "s1_rows", "s1_table";
  * "s1_variant" (1 = class tables of local_map_creation) is the one that selects behaviour.  The same
  * switches are read once from the environment by sgtd_create (SGTD_VOTE_MODE=stream, SGTD_JOIN_GROUPS,
  * SGTD_COLLECT_MODE=desc|inv, SGTD_COLLECT_GROUP, SGTD_DEBUG_NOVOTE); sgtd_search never reads the
