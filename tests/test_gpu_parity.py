@@ -131,7 +131,7 @@ def test_vote_formulations_agree(world, built):
     for opt in ({}, {"join_impl": 0}, {"join_impl": 2}, {"vote_stream": 1}, {"join_groups": 3},
                 {"join_groups": 3, "join_impl": 0}, {"join_groups": 5, "join_impl": 2}, {"collect_mode": 2},
                 {"join_parts": 2}, {"join_parts": 4, "join_groups": 3}, {"join_parts": 3, "join_hint": 1},
-                {"join_hint": 1, "join_groups": 2}, {"verify_impl": 1}):
+                {"join_hint": 1, "join_groups": 2}, {"verify_impl": 1}, {"verify_impl": 3}, {"verify_impl": 4}):
         for k in names:
             mgr.set_option(k, opt.get(k, 1 if k == "join_impl" else 0))
         res = mgr.search(qb)
