@@ -933,7 +933,9 @@ __global__ void __launch_bounds__(kVoteThreads, 3) k_vote_run(RunParams P) {
 constexpr size_t kRunSmem = sizeof(uint64_t) * kRunWarps * kRunSlots * (kJ8Tile + 2) + sizeof(uint4) * kRunWarps * 32 * 3;
 
 // ============================ top-k ==============================================
-constexpr int kTopkThreads = 1024;
+// CTA size of k_topk: 1,024 threads for long vote rows (at most two rows per SM are then in flight: the
+// three to four passes over a row hit L2 instead of DRAM), 256 for short ones (sharded databases)
+constexpr int kTopkLongRow = 65536;
 constexpr int kMaxCand = 256;
 
 __device__ __forceinline__ unsigned long long composite(uint32_t votes, uint32_t frame) {
@@ -941,7 +943,7 @@ __device__ __forceinline__ unsigned long long composite(uint32_t votes, uint32_t
   return ((unsigned long long)votes << 32) | (unsigned long long)(0xFFFFFFFFu - frame);
 }
 
-template <typename T>
+template <int kTopkThreads, typename T>
 __device__ __forceinline__ T block_sum(T v, T *s_tmp) {
   // 256-thread block reduction, result broadcast
 #pragma unroll
@@ -961,6 +963,7 @@ __device__ __forceinline__ T block_sum(T v, T *s_tmp) {
 // rows > T are taken, ties at T are taken in ascending frame order.
 // m_counter (optional): += the sum of the row, i.e. the number of matches of the query (the join casts
 // its votes with predicated REDs and leaves the counting to this pass, which reads every row anyway)
+template <int kTopkThreads>
 __global__ void __launch_bounds__(kTopkThreads) k_topk(const uint32_t *votes, int64_t F, uint32_t frame_lo, int k,
                                                        int32_t *out_votes, int32_t *out_frames,
                                                        unsigned long long *m_counter) {
@@ -977,7 +980,7 @@ __global__ void __launch_bounds__(kTopkThreads) k_topk(const uint32_t *votes, in
   unsigned long long msum = 0;
   for (int64_t f = tid; f < F; f += kTopkThreads) { const uint32_t v = row[f]; n5 += v >= 5u; msum += v; vmax = max(vmax, v); }
   if (tid == 0) s_vmax = 0;
-  n5 = block_sum<uint32_t>(n5, s_tmp);
+  n5 = block_sum<kTopkThreads, uint32_t>(n5, s_tmp);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
   if ((tid & 31) == 0) atomicMax(&s_vmax, vmax);
@@ -2176,8 +2179,10 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
   SGTD_CUDA(h, cudaEventRecord(ev[1], st));
   const int vote_launches = (int)(h->launches - launches0);
   if (nq > 0) {
-    k_topk<<<nq, kTopkThreads, 0, st>>>(r->votes.p, Fa, (uint32_t)h->frame_lo(), k, lv, lf,
-                                        m_by_topk ? r->counters.p + 4 : nullptr);
+    if (Fa >= kTopkLongRow)
+      k_topk<1024><<<nq, 1024, 0, st>>>(r->votes.p, Fa, (uint32_t)h->frame_lo(), k, lv, lf, m_by_topk ? r->counters.p + 4 : nullptr);
+    else
+      k_topk<256><<<nq, 256, 0, st>>>(r->votes.p, Fa, (uint32_t)h->frame_lo(), k, lv, lf, m_by_topk ? r->counters.p + 4 : nullptr);
     SGTD_LAUNCHED(h);
     SGTD_CUDA(h, cudaGetLastError());
   }
