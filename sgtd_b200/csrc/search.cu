@@ -277,7 +277,7 @@ struct EmitParams2 {
 // of all of them are in flight together, and the output cursor -- one address for the whole grid -- is
 // advanced once per trip instead of once per descriptor.
 constexpr int kEmitBatch = 4;
-__global__ void __launch_bounds__(kVoteThreads) k_probe_emit(EmitParams2 P) {
+__global__ void __launch_bounds__(kVoteThreads, 4) k_probe_emit(EmitParams2 P) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * kVoteThreads + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * kVoteThreads) >> 5;
