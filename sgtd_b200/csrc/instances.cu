@@ -950,10 +950,13 @@ __global__ void __launch_bounds__(kCcThreads) k_dcvc_replay_cc(S1Buffers B, cons
 static size_t cc_smem(int cap) { return (size_t)cap * 7 + 16 + (size_t)kCcWarps * kCcRing * sizeof(int2); }
 
 // ---- K5: final label per point, per-label size and first point, compact label list -------
-__global__ void __launch_bounds__(kS1Threads) k_s1_finish(S1Buffers B) {
-  __shared__ int s_warp[kS1Threads / 32];
+// (kThreads: 256 for tasks of up to kPrepSplit points, 1024 above -- as k_dcvc_prepare)
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) k_s1_finish(S1Buffers B) {
+  __shared__ int s_warp[kThreads / 32];
   __shared__ long long s_pool;
   const Task t = B.tasks[blockIdx.x];
+  if ((kThreads == kS1Threads) != (t.npts <= kPrepSplit)) return;
   const int tid = threadIdx.x;
   int *count = B.count + t.lab_off, *first = B.first + t.lab_off;
   int nlab = 0;
@@ -961,7 +964,7 @@ __global__ void __launch_bounds__(kS1Threads) k_s1_finish(S1Buffers B) {
     const TaskState ts = B.ts[blockIdx.x];
     const int *parent = B.parent + t.lab_off;
     const int *t_coord = B.t_coord + t.tab_off, *t_label = B.t_label + t.tab_off;
-    for (int r = tid; r < t.npts; r += kS1Threads) {
+    for (int r = tid; r < t.npts; r += kThreads) {
       const int v = B.slot[t.idx_off + r];
       const bool vis = (__ldcg(t_coord + v) >> 21) <= ts.height;
       const int raw = vis ? __ldcg(t_label + v) : B.pt_label[t.idx_off + r];
@@ -972,7 +975,7 @@ __global__ void __launch_bounds__(kS1Threads) k_s1_finish(S1Buffers B) {
     }
     nlab = ts.labelCount + 1;
   } else if (t.policy == P_GTINST) {
-    for (int r = tid; r < t.npts; r += kS1Threads) {
+    for (int r = tid; r < t.npts; r += kThreads) {
       const int lab = (int)(B.labels[t.pt0 + B.cls_idx[t.idx_off + r]] >> 16);
       B.final_label[t.idx_off + r] = lab;
       atomicAdd(&count[lab], 1);
@@ -980,23 +983,23 @@ __global__ void __launch_bounds__(kS1Threads) k_s1_finish(S1Buffers B) {
     }
     nlab = 65536;
   } else {
-    for (int r = tid; r < t.npts; r += kS1Threads) B.final_label[t.idx_off + r] = 0;
+    for (int r = tid; r < t.npts; r += kThreads) B.final_label[t.idx_off + r] = 0;
     if (tid == 0) { count[0] = t.npts; first[0] = 0; }
     nlab = 1;
   }
   __syncthreads();
   // distinct labels -> pool (label, count, first); order is fixed on the host
   int mine = 0;
-  for (int l = tid; l < nlab; l += kS1Threads) mine += __ldcg(&count[l]) > 0;
+  for (int l = tid; l < nlab; l += kThreads) mine += __ldcg(&count[l]) > 0;
   int total;
-  int pos = block_excl_scan(mine, s_warp, total);
+  int pos = block_excl_scan<kThreads>(mine, s_warp, total);
   if (tid == 0) {
     s_pool = (long long)atomicAdd(B.pool_cursor, (unsigned long long)total);
     B.ts[blockIdx.x].pool_off = s_pool;
     B.ts[blockIdx.x].ndistinct = total;
   }
   __syncthreads();
-  for (int l = tid; l < nlab; l += kS1Threads) {
+  for (int l = tid; l < nlab; l += kThreads) {
     const int c = __ldcg(&count[l]);
     if (c > 0) {
       int *o = B.pool + 3 * (s_pool + pos);
@@ -1317,7 +1320,8 @@ int extract_instances(sgtd_handle *h, const float4 *d_pts, const uint32_t *d_lab
         for (int c = 0; c < 4; ++c) S1_CUDA(cudaStreamWaitEvent(st, sp.ev[1 + c], 0));
     }
     trace("replay");
-    k_s1_finish<<<nt, kS1Threads, 0, st>>>(B);
+    k_s1_finish<kS1Threads><<<nt, kS1Threads, 0, st>>>(B);
+    k_s1_finish<1024><<<nt, 1024, 0, st>>>(B);
     h->launches += 16;
     S1_CUDA(cudaGetLastError());
     // The label pool goes to the host on a side stream; meanwhile the main stream lists every would-be node
