@@ -827,6 +827,7 @@ __global__ void __launch_bounds__(kCcThreads) k_dcvc_replay_cc(S1Buffers B, cons
       for (int j = 0; j < 4; ++j) { const int i = base + 32 * j + lane; pre[j] = i < nev ? evc[i] : make_int2(0, 0); }
     };
     auto commit = [&]() {
+      __syncwarp();  // the slots overwritten here were read (windows 256 events back) by every lane
 #pragma unroll
       for (int j = 0; j < 4; ++j) ring[(pre_base + 32 * j + lane) & (kCcRing - 1)] = pre[j];
       loaded = min(nev, pre_base + 128);
