@@ -1780,7 +1780,7 @@ __global__ void __launch_bounds__(kVerifyThreads, kMinBlocks) k_verify(VerifyPar
       }
       mgc = fminf(fmaf(4.0e-5f, mx, 1.0e-4f), 8.0f);  // margin of the couple
     }
-#pragma unroll(kMinBlocks == 4 ? 2 : (kMinBlocks == 3 ? 4 : 1))
+#pragma unroll(kMinBlocks == 4 ? 2 : 1)
     for (int h = 0; h < H; ++h) {
       const float4 p0 = *reinterpret_cast<const float4 *>(&s_posef[h][0]), p1 = *reinterpret_cast<const float4 *>(&s_posef[h][4]),
                    p2 = *reinterpret_cast<const float4 *>(&s_posef[h][8]);
@@ -2234,18 +2234,15 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
       SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem_max));
       SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem_max));
       SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem_max));
-      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem_max));
-      SGTD_CUDA(h, cudaFuncSetAttribute(k_collect_inv<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem_max));
       for (int qb0 = 0; qb0 < nq; qb0 += qt_group) {
         const int gq = std::min(qt_group, nq - qb0);
         k_query_index<<<gq, kIndexThreads, 0, st>>>(qb->rec.p, aux, qb->d_off.p, qb0, (uint32_t *)(S + o_qtk), qt_ts,
                                                     (const uint32_t *)(S + o_qpr), r->cands.p, k);
         I.q_base = qb0;
-        // (measured on the bench workload: 1 hit per thread and trip 5.0 ms, 2: 5.6, 4: 7.2 -- occupancy wins)
+        // (measured on the bench workload: 1 hit per thread and trip at 4 CTAs/SM 5.0 ms, 2 hits at 3 CTAs/SM 5.6,
+        // 4 hits at 2 CTAs/SM 7.2; 1 hit at 5 / 6 CTAs/SM (48 / 40 registers) 5.0 / 5.5 -- occupancy wins up to 4)
         if (h->opt.collect_unroll == 4) k_collect_inv<4, 2><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
         else if (h->opt.collect_unroll == 2) k_collect_inv<2, 3><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
-        else if (h->opt.collect_unroll == 5) k_collect_inv<1, 5><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
-        else if (h->opt.collect_unroll == 6) k_collect_inv<1, 6><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
         else k_collect_inv<1, 4><<<(unsigned)gq * k, kCollectThreads, inv_smem, st>>>(I);
         h->launches += 2;
       }
@@ -2268,10 +2265,8 @@ int search(sgtd_handle *h, const sgtd_desc_batch *qb, sgtd_search_result *r) {
     k_hypotheses<<<(unsigned)(((size_t)nslot * kMaxHyp + 127) / 128), 128, 0, st>>>(W, (int)nslot);
     SGTD_LAUNCHED(h);
     // default: hypothesis loop unrolled by 2 at 4 CTAs/SM (measured 9.00 ms on the bench workload; not unrolled at
-    // 5 CTAs/SM: 9.26, at 6 CTAs/SM with 80 registers: 9.54)
-    if (h->opt.verify_impl == 1) k_verify<6><<<(unsigned)nslot, kVerifyThreads, 0, st>>>(W);
-    else if (h->opt.verify_impl == 3) k_verify<5><<<(unsigned)nslot, kVerifyThreads, 0, st>>>(W);
-    else if (h->opt.verify_impl == 4) k_verify<3><<<(unsigned)nslot, kVerifyThreads, 0, st>>>(W);
+    // 5 CTAs/SM -- option verify_impl = 3 -- 9.26; at 6 CTAs/SM with 80 registers 9.54; unrolled by 4 at 3 CTAs/SM 8.97)
+    if (h->opt.verify_impl == 3) k_verify<5><<<(unsigned)nslot, kVerifyThreads, 0, st>>>(W);
     else k_verify<4><<<(unsigned)nslot, kVerifyThreads, 0, st>>>(W);
     SGTD_LAUNCHED(h);
     SGTD_CUDA(h, cudaGetLastError());

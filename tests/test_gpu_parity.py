@@ -127,11 +127,11 @@ def test_vote_formulations_agree(world, built):
     qb = mgr.build(capi.make_nodes(qx, ql), qo)
     F = o.current_frame_id
     ref = None
-    names = ("vote_stream", "join_groups", "collect_mode", "join_impl", "join_parts", "join_hint", "verify_impl")
+    names = ("vote_stream", "join_groups", "collect_mode", "join_impl", "join_parts", "join_hint", "verify_impl", "collect_unroll")
     for opt in ({}, {"join_impl": 0}, {"join_impl": 2}, {"vote_stream": 1}, {"join_groups": 3},
                 {"join_groups": 3, "join_impl": 0}, {"join_groups": 5, "join_impl": 2}, {"collect_mode": 2},
                 {"join_parts": 2}, {"join_parts": 4, "join_groups": 3}, {"join_parts": 3, "join_hint": 1},
-                {"join_hint": 1, "join_groups": 2}, {"verify_impl": 1}, {"verify_impl": 3}, {"verify_impl": 4}):
+                {"join_hint": 1, "join_groups": 2}, {"verify_impl": 3}, {"collect_unroll": 2}, {"collect_unroll": 4}):
         for k in names:
             mgr.set_option(k, opt.get(k, 1 if k == "join_impl" else 0))
         res = mgr.search(qb)
