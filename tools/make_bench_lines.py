@@ -24,9 +24,9 @@ def row(name, d):
 out = ["# Round 2 (second half) bench lines (builder runs on the GPU box, `gpurun_out/r02b_*`)\n"]
 out.append("All lines: BASELINE.json configs[3], 100k-keyframe synthetic city DB (239.47 M descriptors), 1,024-query batch, f64, "
            f"`result_crc` {n1['result_crc']} in every layout, `parity_checked` true (join == exact streaming kernel on a warm-up step), "
-           "1,024 / 1,024 queries localised (T < 5 m, R < 10 deg), SM clocks 1965 / 1965 MHz, no throttle reasons.  The N=1 line is the "
-           "committed code; the multi-GPU lines were taken two small kernel changes earlier (probe emission and vote join "
-           "occupancy, -0.4 ms per N=1 step).\n")
+           "1,024 / 1,024 queries localised (T < 5 m, R < 10 deg), SM clocks 1965 / 1965 MHz, no throttle reasons.  The N=1 / 2 / 4 / 8 lines of "
+           "the default layout are the committed code; the replica-layout lines (`--shards`) were taken two small kernel changes "
+           "earlier (probe emission and vote join occupancy, -0.4 ms per N=1 step).\n")
 out.append("| run | queries/s (device) | e2e queries/s | ms/step | stage ms (probe / vote / topk / exchange / collect / verify) |\n|---|---|---|---|---|")
 out.append(row("N=1 `python bench.py --steps 20 --warmup 5`", n1))
 out.append(row("N=2 torchrun (keyframe-range x2)", n2))
