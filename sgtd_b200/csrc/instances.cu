@@ -17,14 +17,19 @@
 //     = height+1, skipped by every walk including their own) seed individually;
 //   * the O(N) relabel sweep is a union-find link  parent[cur] = neigh.
 // So: a fully parallel pass (polar transform, curved-voxel open-addressing table with
-// atomicCAS/atomicMin, event list by ordered compaction), then one warp per
-// (scan, class) task replays the event list: lanes 0..26 look the 27 neighbour voxels
-// up in parallel, lane 0 applies the walk.  Many tasks run concurrently (one scan has
-// ~8 class tasks; a batch of scans fills the machine).
+// atomicCAS/atomicMin, event list by ordered compaction), a second one that writes every voxel's 27-neighbour
+// row, and then the replay of the event list per (scan, class) task.  Events of different connected
+// components of the voxel-neighbour graph commute, so the default replay (k_dcvc_replay_cc) finds the
+// components with a 16-bit union-find and lets the 8 warps of the task's CTA replay them concurrently; new
+// labels are named after the event that creates them and renamed to the reference's counter values by a
+// prefix sum afterwards.  Oversized tasks use the sequential forms (k_dcvc_replay: one replaying warp, lanes
+// 0..26 = the 27 neighbours).  Many tasks run concurrently (one scan has ~8 class tasks; a batch of scans
+// fills the machine).
 // The cluster -> instance-id order is the iteration order of the reference's
 // std::unordered_map<int, vector<int>> (cluster_manager.hpp:395-418); it is reproduced
 // on the host with the real container fed the labels in first-appearance order.
-// Centroids are sequential float32 sums in ascending point order (get_json.cpp:266-274).
+// Centroids are sequential float32 sums in ascending point order (get_json.cpp:266-274); they are summed per
+// label on the GPU while the host works out the instance order.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
