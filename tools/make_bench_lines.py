@@ -67,5 +67,14 @@ out.append(f"`bench.py --workload seq` (configs[1]-shaped, 1,024-scan map, 256 q
            f"{seq['e2e']['value']:.0f} from host memory (576 MB of points H2D per step; the library's small copies queue behind a caller's prefetch on the H2D copy "
            f"engine, so double buffering from the caller did not overlap -- measured); per step stage 1 {st['stage1_ms']} ms, stage 2 {st['stage2_ms']}, stages 3-4 "
            f"{st['stage34_ms']}; 256 / 256 localised.  Start of the round: 5,597 / 4,560 scans/s (stage 1 41 ms).\n")
+try:
+    full = load("r02b_seq_4541.json")
+    sf = full["stage_ms_per_step"]
+    out.append(f"Same workload at the full configs[1] map size (`--scans 4541`, map built from 4,541 scans in {full['config']['map_build_s']} s = "
+               f"{4541 / full['config']['map_build_s']:.0f} scans/s through stages 1-2 + add, not timed): {full['value']:.0f} scans/s device-resident, "
+               f"{full['e2e']['value']:.0f} from host memory; per step stage 1 {sf['stage1_ms']} ms, stage 2 {sf['stage2_ms']}, stages 3-4 {sf['stage34_ms']}; "
+               f"{full['recall']['success_T5m_R10deg']} / {full['recall']['queries']} localised.\n")
+except FileNotFoundError:
+    pass
 open("profiles/r02b_bench_lines.md", "w").write("\n".join(out))
 print("\n".join(out[:14]))
