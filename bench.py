@@ -82,6 +82,21 @@ def parse():
     return ap.parse_args()
 
 
+def plan_layout(rank, world, shards, nkf, nq):
+    """S keyframe-range shards x R = world / S replica groups.  Group g = ranks g*S .. g*S+S-1 holds the
+    whole database once (shard s = keyframes [s*fpr, (s+1)*fpr)) and serves queries [g*nq/R, (g+1)*nq/R).
+    shards = 0 means S = world: one shard per GPU, every GPU votes the whole batch (BASELINE.json configs[3])."""
+    S = shards if shards > 0 else world
+    if world % S:
+        raise ValueError("--shards must divide the number of GPUs")
+    R = world // S
+    grp, srank = rank // S, rank % S
+    fpr = (nkf + S - 1) // S
+    lo, hi = (srank * fpr, min(nkf, (srank + 1) * fpr)) if S > 1 else (0, nkf)
+    return {"S": S, "R": R, "group": grp, "shard_rank": srank, "frames_per_rank": fpr, "frame_lo": lo, "frame_hi": max(hi, lo),
+            "query_lo": grp * nq // R, "query_hi": (grp + 1) * nq // R}
+
+
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
@@ -472,24 +487,19 @@ def run_ours(args):
     # layout: S keyframe-range shards x R = N / S replicas; replica group g (ranks g*S .. g*S+S-1) serves
     # queries [g*nq/R, (g+1)*nq/R) against its own copy of the S shards.  Default S = N (R = 1): every GPU
     # holds one shard and votes the whole batch (BASELINE.json configs[3]).
-    S = args.shards if args.shards > 0 else world
-    assert world % S == 0, "--shards must divide the number of GPUs"
-    R = world // S
-    grp, srank = rank // S, rank % S
-    fpr = (nkf + S - 1) // S
+    L = plan_layout(rank, world, args.shards, nkf, nq)
+    S, R, grp, srank, fpr = L["S"], L["R"], L["group"], L["shard_rank"], L["frames_per_rank"]
     if S > 1:
         mine = torch.from_numpy(capi.nccl_unique_id()).to(dev)
         ids = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(ids, mine)                 # the id of a group is its leader's
         mgr.shard_init(srank, S, fpr, ids[grp * S].cpu().numpy())
-    lo, hi = (srank * fpr, min(nkf, (srank + 1) * fpr)) if S > 1 else (0, nkf)
+    lo, hi = L["frame_lo"], L["frame_hi"]
+    q0, q1, nq_all = L["query_lo"], L["query_hi"], nq
     if R > 1:
-        q0, q1 = grp * nq // R, (grp + 1) * nq // R
         qx, ql = qx[qo[q0]:qo[q1]], ql[qo[q0]:qo[q1]]
         qo = (qo[q0:q1 + 1] - qo[q0]).astype(np.int64)
-        nq_all, nq = nq, q1 - q0
-    else:
-        q0, nq_all = 0, nq
+        nq = q1 - q0
 
     # ---- database build (not timed): stage 2 on the GPU for this rank's keyframes ----
     t0 = time.time()
